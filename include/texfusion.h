@@ -1,0 +1,238 @@
+/*
+ * texfusion.h — C ABI of libtexfusion_b200.so
+ *
+ * B200-native (sm_100a) replacement for the per-frame fusion hot path of
+ * THU-luvision/TextureFusion (FlashFusion).  The reference has no FFI layer: its boundary
+ * is the public C++ surface of chisel::Chisel / ChunkManager / ProjectionIntegrator / Atlas
+ * called from GCFusion/MobileFusion.cpp.  Each entry point below names the reference
+ * interface (file:line, relative to the reference tree) whose work it takes over; the C++
+ * shim in texturefusion_b200/host/ keeps those class/method names on top of this ABI
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain pointers + sizes, POD structs, no C++/torch types, no exceptions.
+ *   - every function returns 0 on success, <0 on error (tf_last_error gives the text);
+ *     functions that are pure queries say so.
+ *   - a tf_map is not thread-safe; one caller thread at a time (the reference's map
+ *     thread, GCFusion/MobileFusion.cpp:99-112).  All device work of one map runs on one
+ *     CUDA stream; a call returns once the results it hands to the host are visible.
+ *   - image pointers are borrowed for the duration of the call.  Pinned host memory
+ *     (tf_host_alloc) is DMA'd directly; pageable memory is staged.
+ *   - there is NO CPU fallback: without a CUDA device tf_create fails with TF_ERR_CUDA.
+ */
+#ifndef TEXFUSION_B200_H
+#define TEXFUSION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TF_ABI_VERSION 1
+
+enum {
+  TF_OK = 0,
+  TF_ERR_INVALID = -1,    /* bad argument                                   */
+  TF_ERR_CUDA = -2,       /* CUDA runtime error / no device                 */
+  TF_ERR_CAPACITY = -3,   /* chunk pool, candidate grid or out buffer full  */
+  TF_ERR_NOT_FOUND = -4,  /* unknown frame_index or chunk id (ref: unordered_map::at throws,
+                             Structure/ChunkManager.h:137-139)              */
+  TF_ERR_ATLAS_FULL = -5  /* ref: std::overflow_error in Atlas::AddPatch, Structure/Atlas.cpp:52-53 */
+};
+
+typedef struct tf_map tf_map; /* opaque: one volumetric map on one GPU (one rank) */
+
+/* == Eigen::Vector3i layout; chisel::ChunkID (3rd_party/open_chisel/geometry/Geometry.h) */
+typedef struct { int32_t x, y, z; } tf_chunk_id;
+
+/* chisel::PinholeCamera (3rd_party/open_chisel/camera/PinholeCamera.h:33-75).  Pass the
+ * float intrinsics given to SetIntrinsics; the library applies the int truncation of
+ * GetFx/GetFy/GetCx/GetCy (:46-49) itself. */
+typedef struct {
+  float fx, fy, cx, cy;
+  int32_t width, height;
+  float near_plane, far_plane;
+} tf_camera;
+
+/* QuadraticTruncator(quad, lin, cst, scale) + ConstantWeighter(weight)
+ * (GCFusion/MobileFusion.h:215-228). */
+typedef struct { float quad, lin, cst, scale, weight; } tf_truncation;
+
+/* chisel::Transform == Eigen::Affine3f, column-major 4x4, camera -> world
+ * (pose_sophus[k].matrix().cast<float>(), GCFusion/MobileFusion.cpp:133,136). */
+typedef struct { float m[16]; } tf_pose;
+
+typedef struct {
+  int32_t chunk_dim;      /* voxels per chunk edge; only 8 is supported (GCFusion/MobileFusion.h:231-233) */
+  float voxel_res;        /* metres */
+  int32_t use_color;      /* chisel::Chisel ctor arg (GCFusion/MobileFusion.h:239-241) */
+  tf_truncation trunc;
+  int32_t device;         /* CUDA ordinal */
+  int32_t n_ranks, rank;  /* chunk sharding: this map owns chunks with owner(id) == rank */
+  int64_t max_chunks;     /* chunk-pool capacity (8 KiB each); 0 = default */
+  int32_t max_frames;     /* frame-store slots; 0 = default */
+  int32_t width, height;  /* frame size of the store; 0 = 640x480 */
+} tf_config;
+
+/* chisel::Chisel::Chisel + ChunkManager ctor (Structure/Chisel.cpp:38-41). */
+int tf_create(tf_map** out, const tf_config* cfg);
+void tf_destroy(tf_map* m);
+/* text of the last error on this map (m == NULL: last tf_create failure). Query. */
+const char* tf_last_error(const tf_map* m);
+/* Chisel::Reset (Structure/Chisel.cpp:47-50): drop all chunks, keep frames and atlas. */
+int tf_reset(tf_map* m);
+
+/* pinned host memory for frame / result buffers */
+void* tf_host_alloc(size_t bytes);
+void tf_host_free(void* p);
+
+/* ---- frame store ---------------------------------------------------------------------
+ * Frame::refined_depth / RGBA packed by ReIntegrateKeyframe / observationQualityMap
+ * (GCSLAM/frame.h:35-66, GCFusion/MobileFusion.cpp:147-162).  depth: float32 metres,
+ * width*height; rgba: 4 bytes per pixel, A = colour-valid (1/0); quality: float32.
+ * rgba/quality may be NULL (depth-only local frame, GCFusion/MobileFusion.cpp:198-202).
+ * Re-uploading a frame_index overwrites it. */
+int tf_upload_frame(tf_map* m, int32_t frame_index, const float* depth,
+                    const uint8_t* rgba_or_null, const float* quality_or_null);
+/* Key-frame colour as the reference stores it: Frame::rgb (8UC3) + colorValidFlag (8U).
+ * Keeps rgb for the atlas (Patch::SetImage, Structure/Patch.cpp:172-175) and packs the
+ * RGBA plane on the device — replaces the scalar pack loop GCFusion/MobileFusion.cpp:151-162
+ * (color_valid == NULL: alpha = 1 everywhere, as IntegrateFrame :237-242). */
+int tf_upload_keyframe_rgb(tf_map* m, int32_t frame_index, const uint8_t* rgb,
+                           const uint8_t* color_valid_or_null);
+int tf_release_frame(tf_map* m, int32_t frame_index);
+/* Device addresses of a frame's planes (allocating the slot if needed) so that a
+ * collective (NCCL broadcast over NVLink) can land directly in the store.  Any out
+ * pointer may be NULL.  has_color != 0 marks rgba/quality as present. */
+int tf_frame_device_ptrs(tf_map* m, int32_t frame_index, int has_color, void** depth,
+                         void** rgba, void** quality);
+
+/* ---- per-frame hot path -------------------------------------------------------------- */
+
+/* Chisel::PrepareIntersectChunks (Structure/Chisel.h:103-140): depth bbox
+ * (ChunkManager::GetBoundaryChunkID, Structure/ChunkManager.h:366-378), coarse/fine
+ * culling (GetChunkIDsObservedByCamera, :380-559) and HasChunk/CreateChunk for every hit.
+ * ids_out is in the reference's traversal order; is_new_out[i] in {0,1}.  If more than cap
+ * chunks are hit, *n_out is the required size and TF_ERR_CAPACITY is returned (the map is
+ * then unchanged).  With n_ranks > 1 only chunks owned by this rank are listed. */
+int tf_prepare(tf_map* m, int32_t frame_index, const tf_pose* pose, const tf_camera* cam,
+               tf_chunk_id* ids_out, uint8_t* is_new_out, int64_t cap, int64_t* n_out);
+
+/* Chisel::IntegrateDepthScanColor, list form (Structure/Chisel.h:218-249) ->
+ * ProjectionIntegrator::voxelUpdateSIMD (3rd_party/open_chisel/utils/ProjectionIntegrator.cpp:67-426).
+ * flag 1 = integrate, 0 = de-integrate.  needs_update_inout[i] |= updated.
+ * quality_out_or_null[i] = the chunk's raw chunkObservationQuality (only meaningful when
+ * use_color and the frame has a quality plane); the caller applies
+ * `keyframeID >= 0 && q > 0 && needsUpdate` (Structure/Chisel.h:244-247). */
+int tf_integrate(tf_map* m, int32_t frame_index, int use_color, const tf_pose* pose,
+                 const tf_camera* cam, const tf_chunk_id* ids, int64_t n, int flag,
+                 uint8_t* needs_update_inout, float* quality_out_or_null);
+
+/* One group of frames applied, in order, to ONE chunk list with the voxels held in
+ * registers (a key-frame followed by its local depth frames,
+ * GCFusion/MobileFusion.cpp:176-203).  Same result as n_frames tf_integrate calls. */
+typedef struct {
+  int32_t frame_index;
+  int32_t use_color;
+  int32_t flag; /* 1 integrate, 0 de-integrate */
+  int32_t reserved;
+  tf_pose pose;
+} tf_group_frame;
+int tf_integrate_group(tf_map* m, const tf_group_frame* frames, int32_t n_frames,
+                       const tf_camera* cam, const tf_chunk_id* ids, int64_t n,
+                       uint8_t* needs_update_inout, float* quality_out_or_null /* frame 0 */);
+
+/* Device half of Chisel::FinalizeIntegrateChunks / GarbageCollect
+ * (Structure/Chisel.h:184-216,472-477): ChunkManager::RemoveChunk for each id. */
+int tf_remove_chunks(tf_map* m, const tf_chunk_id* ids, int64_t n);
+
+/* Chisel::IntegrateDepthScanColor, convenience form (Structure/Chisel.h:453-468) =
+ * Prepare + Integrate(flag 1) + Finalize, as MobileFusion::IntegrateFrame uses it
+ * (GCFusion/MobileFusion.cpp:223-250) — fused: no host round trip between the stages.
+ * Outputs (any may be NULL; cap = capacity of each array): the intersecting list, its
+ * new/updated flags and the raw quality sums.  Never-updated new chunks are already
+ * removed on return; the caller derives meshesToUpdate / validChunks from `updated`. */
+typedef struct {
+  int64_t n_chunks;        /* |chunksIntersecting| */
+  int64_t n_new;           /* created by this frame */
+  int64_t n_updated;       /* needsUpdate == true */
+  int64_t n_removed;       /* new && !updated -> garbage collected */
+  int64_t voxel_updates;   /* 512 * n_chunks */
+} tf_frame_stats;
+int tf_integrate_frame(tf_map* m, int32_t frame_index, int use_color, const tf_pose* pose,
+                       const tf_camera* cam, tf_frame_stats* stats_out, tf_chunk_id* ids_out,
+                       uint8_t* is_new_out, uint8_t* updated_out, float* quality_out, int64_t cap);
+
+/* Loop-closure path (GCFusion/MobileFusion.cpp:301-310): one item = one
+ * ReIntegrateKeyframe call (:114-221).  flag 0: de-integrate the key-frame and its local
+ * frames with their old poses over `ids` (= kf.validChunks).  flag 1: Prepare with the
+ * key-frame's depth under its new pose, integrate the group, Finalize; the new valid list
+ * is written to valid_out (cap entries) / *n_valid_out. */
+typedef struct {
+  int32_t flag;
+  int32_t n_frames;               /* 1 key-frame + local frames */
+  const tf_group_frame* frames;   /* frames[0] is the key-frame */
+  const tf_chunk_id* ids;         /* flag 0: chunk list to de-integrate */
+  int64_t n_ids;
+  tf_chunk_id* valid_out;         /* flag 1 */
+  float* quality_out;             /* flag 1: raw quality sum per valid_out entry (or NULL) */
+  int64_t cap;
+  int64_t* n_valid_out;
+} tf_batch_item;
+int tf_integrate_batch(tf_map* m, const tf_batch_item* items, int64_t n_items,
+                       const tf_camera* cam);
+
+/* ---- chunk map queries (ChunkManager::HasChunk/GetChunks, Structure/ChunkManager.h:126-139) */
+int tf_has_chunk(tf_map* m, tf_chunk_id id);  /* 1 / 0, <0 on error */
+int64_t tf_chunk_count(tf_map* m);
+int tf_list_chunks(tf_map* m, tf_chunk_id* out, int64_t cap, int64_t* n_out);
+/* Read-back for the CPU mesher (Structure/ChunkManager.cpp:614-626) and for parity:
+ * sdf[512], weight[512], color[2048] per chunk in the reference layout
+ * (voxel = (z*8+y)*8+x, 3rd_party/open_chisel/geometry/Chunk.h:91-93). */
+int tf_download_chunks(tf_map* m, const tf_chunk_id* ids, int64_t n, float* sdf,
+                       float* weight, uint16_t* color);
+
+/* ---- texture atlas (Structure/Atlas.{h,cpp}) ---------------------------------------- */
+/* Atlas::AddPatch placement (Structure/Atlas.cpp:43-64): first call for an id hands out
+ * loc_next and advances it; later calls return the same texloc. */
+int tf_atlas_alloc_slot(tf_map* m, tf_chunk_id id, uint64_t* texloc_out);
+/* Atlas::UpdateBuffer (Structure/Atlas.cpp:71-91) for a batch of patches: crop
+ * (x,y,w,h) of key-frame frame_index's rgb (cv::Rect semantics, Patch::SetImage) is copied
+ * to the slot at texloc, or bilinearly resized (cv::resize INTER_LINEAR) to the slot size
+ * when it does not fit. */
+typedef struct {
+  uint64_t texloc;
+  int32_t frame_index;
+  int32_t x, y, w, h;
+} tf_patch_desc;
+int tf_atlas_update(tf_map* m, const tf_patch_desc* patches, int64_t n);
+/* texture_buffer rows for the GL upload (GCFusion/MobileFusion.h:404-427): bytes
+ * [hot_start*3, hot_end*3) of the 13824x13824x3 atlas, hot_* in pixels as Atlas::hot_start. */
+int tf_atlas_download(tf_map* m, uint64_t hot_start, uint64_t hot_end, uint8_t* rgb_out);
+int tf_atlas_patch_size(tf_map* m, int32_t* patch_w, int32_t* patch_h);
+
+/* ---- misc ---------------------------------------------------------------------------- */
+int tf_sync(tf_map* m);
+/* counters since creation: kernels launched by this library, bytes moved each way */
+typedef struct {
+  int64_t kernel_launches;
+  int64_t h2d_bytes, d2h_bytes;
+  int64_t frames_integrated;
+  int64_t voxel_updates;
+  int64_t pool_capacity, pool_used;
+} tf_counters;
+int tf_get_counters(tf_map* m, tf_counters* out);
+/* CUDA stream of the map as a cudaStream_t cast to void* (for event timing by the caller) */
+void* tf_stream(tf_map* m);
+/* device time (ms) spent in the integrate kernel since the last call with reset != 0;
+ * measured with CUDA events on the map's stream when enabled via tf_set_profiling. */
+int tf_set_profiling(tf_map* m, int enable);
+int tf_get_kernel_time(tf_map* m, int reset, double* integrate_ms, int64_t* integrate_launches,
+                       double* integrate_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEXFUSION_B200_H */

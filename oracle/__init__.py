@@ -1,0 +1,6 @@
+"""CPU oracle (TEST INFRASTRUCTURE ONLY — see oracle/tf_oracle.cpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this package.  Nothing under texturefusion_b200/ does.
+"""
+from .oracle import OracleMap, build_oracle, oracle_lib_path  # noqa: F401

@@ -1,0 +1,193 @@
+"""GPU parity: libtexfusion_b200.so (through the C ABI) against the CPU oracle on the same
+seeded synthetic inputs.  Bar: allocated-chunk set and ordering bit-exact, weights and
+colours bit-exact, TSDF within 1e-5 of the truncation distance (in practice bit-exact)."""
+import numpy as np
+import pytest
+
+from oracle import OracleMap
+from texturefusion_b200 import capi
+from texturefusion_b200.chisel import Chisel
+
+from util import RESOLUTIONS, assert_maps_equal, room_sequence, sort_ids
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("res", RESOLUTIONS)
+def test_prepare_matches_oracle_order_and_flags(res):
+    seq = room_sequence(3)
+    cam = seq.cam
+    g = capi.Map(res)
+    o = OracleMap(res)
+    for fr in seq.frames:
+        g.upload_frame(fr.index, fr.depth)
+        gi, gnew = g.prepare(fr.index, fr.pose, cam)
+        oi, onew = o.prepare(fr.depth, fr.pose, cam)
+        assert len(gi) == len(oi) and len(oi) > 0
+        assert np.array_equal(gi, oi), "chunk list (reference traversal order) differs"
+        assert np.array_equal(gnew, onew)
+        assert g.chunk_count() == o.chunk_count()
+    assert_maps_equal(g, o, what=f"prepare res={res}")
+
+
+@pytest.mark.parametrize("res", RESOLUTIONS)
+def test_fused_sequence_bit_exact(res):
+    seq = room_sequence(6)
+    cam = seq.cam
+    g = capi.Map(res)
+    o = OracleMap(res)
+    for fr in seq.frames:
+        rgba = fr.rgba() if fr.is_keyframe else None
+        g.upload_frame(fr.index, fr.depth, rgba, fr.quality if fr.is_keyframe else None)
+        st, ids, new, upd, q = g.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam)
+        n, nupd = o.integrate_frame(fr.depth, rgba, fr.quality, fr.pose, cam, -1)
+        assert st.n_chunks == n and st.n_updated == nupd
+        assert g.chunk_count() == o.chunk_count()
+    exact = assert_maps_equal(g, o, what=f"fused res={res}")
+    assert exact, "TSDF within tolerance but not bit-exact"
+
+
+@pytest.mark.parametrize("res", (0.02, 0.005))
+def test_split_protocol_keyframe_with_local_frames(res):
+    """ReIntegrateKeyframe(flag=1) protocol (GCFusion/MobileFusion.cpp:114-221): Prepare on the
+    key-frame, integrate key-frame with colour + quality, local frames depth-only into the
+    same list, Finalize."""
+    seq = room_sequence(6)
+    cam = seq.cam
+    c = Chisel(voxelResolution=res)
+    o = OracleMap(res)
+    kf, local = seq.frames[0], seq.frames[1:3]
+    ids, nu, new = c.PrepareIntersectChunks(kf.depth, kf.pose, cam)
+    oi, onew = o.prepare(kf.depth, kf.pose, cam)
+    assert np.array_equal(ids, oi) and np.array_equal(new, onew)
+    c.IntegrateDepthScanColor(kf.depth, kf.rgba(), kf.pose, cam, ids, nu, 1, kf.index, kf.quality)
+    onu, oq = o.integrate(kf.depth, kf.rgba(), kf.quality, kf.pose, cam, oi, 1, kf.index)
+    assert np.array_equal(nu, onu)
+    for lf in local:
+        c.IntegrateDepthScanColor(lf.depth, None, lf.pose, cam, ids, nu, 1)
+        onu, _ = o.integrate(lf.depth, None, None, lf.pose, cam, oi, 1, -1, onu)
+        assert np.array_equal(nu, onu)
+    valid = c.FinalizeIntegrateChunks(ids, nu, new)
+    ovalid = o.finalize(oi, onu, onew)
+    assert np.array_equal(valid, ovalid)
+    assert assert_maps_equal(c.map, o, what="split protocol")
+    # observations[keyframe] (Structure/Chisel.h:244-247), consumed by TexMap::update_datacost
+    n_obs = 0
+    for cid in valid[:: max(1, len(valid) // 200)]:
+        want = o.observation(cid, kf.index)
+        got = c.chunkManager.GetChunk(cid).observations.get(kf.index)
+        assert (want is None) == (got is None)
+        if want is not None:
+            assert np.float32(want) == np.float32(got)
+            n_obs += 1
+    assert n_obs > 0
+    # meshesToUpdate set
+    om = {tuple(int(v) for v in r) for r in o.meshes_to_update()}
+    assert om == {k for k, v in c.meshesToUpdate.items() if v}
+
+
+@pytest.mark.parametrize("res", (0.02, 0.005))
+def test_deintegrate_then_reintegrate(res):
+    """Loop-closure step (GCFusion/MobileFusion.cpp:301-310): de-integrate a key-frame with its
+    old pose over kf.validChunks, re-integrate under the corrected pose."""
+    seq = room_sequence(4)
+    cam = seq.cam
+    c = Chisel(voxelResolution=res)
+    o = OracleMap(res)
+    valid_lists = []
+    for fr in seq.frames[:3]:
+        rgba = fr.rgba()
+        ids, nu, new = c.PrepareIntersectChunks(fr.depth, fr.pose, cam)
+        c.IntegrateDepthScanColor(fr.depth, rgba, fr.pose, cam, ids, nu, 1, fr.index, fr.quality)
+        valid = c.FinalizeIntegrateChunks(ids, nu, new)
+        oi, onew = o.prepare(fr.depth, fr.pose, cam)
+        onu, _ = o.integrate(fr.depth, rgba, fr.quality, fr.pose, cam, oi, 1, fr.index)
+        ovalid = o.finalize(oi, onu, onew)
+        assert np.array_equal(valid, ovalid)
+        valid_lists.append(valid)
+    assert assert_maps_equal(c.map, o, what="before de-integration")
+    fr = seq.frames[1]
+    rgba = fr.rgba()
+    vl = valid_lists[1]
+    nu = np.ones(len(vl), np.uint8)
+    c.IntegrateDepthScanColor(fr.depth, rgba, fr.pose, cam, vl, nu, 0, fr.index, fr.quality)
+    c.FinalizeIntegrateChunks(vl, nu, np.zeros(len(vl), np.uint8))
+    onu, _ = o.integrate(fr.depth, rgba, fr.quality, fr.pose, cam, vl, 0, fr.index, np.ones(len(vl), np.uint8))
+    o.finalize(vl, onu, np.zeros(len(vl), np.uint8))
+    assert assert_maps_equal(c.map, o, what="after de-integration")
+    new_pose = fr.pose.copy()
+    new_pose[:3, 3] += np.array([0.004, -0.003, 0.002], np.float32)
+    ids, nu, new = c.PrepareIntersectChunks(fr.depth, new_pose, cam)
+    c.IntegrateDepthScanColor(fr.depth, rgba, new_pose, cam, ids, nu, 1, fr.index, fr.quality)
+    valid = c.FinalizeIntegrateChunks(ids, nu, new)
+    oi, onew = o.prepare(fr.depth, new_pose, cam)
+    onu, _ = o.integrate(fr.depth, rgba, fr.quality, new_pose, cam, oi, 1, fr.index)
+    ovalid = o.finalize(oi, onu, onew)
+    assert np.array_equal(valid, ovalid)
+    assert assert_maps_equal(c.map, o, what="after re-integration")
+
+
+def test_group_equals_sequential_calls():
+    """tf_integrate_group (voxels held in registers across frames) == separate tf_integrate calls."""
+    res = 0.005
+    seq = room_sequence(6)
+    cam = seq.cam
+    a, b = capi.Map(res), capi.Map(res)
+    kf = seq.frames[0]
+    for m in (a, b):
+        for fr in seq.frames[:4]:
+            m.upload_frame(fr.index, fr.depth, fr.rgba() if fr.is_keyframe else None, fr.quality)
+    ids, _ = a.prepare(kf.index, kf.pose, cam)
+    ids_b, _ = b.prepare(kf.index, kf.pose, cam)
+    assert np.array_equal(ids, ids_b)
+    frames = [(kf.index, True, 1, kf.pose)] + [(fr.index, False, 1, fr.pose) for fr in seq.frames[1:4]]
+    nu_a, q_a = a.integrate_group(frames, cam, ids)
+    nu_b = np.zeros(len(ids), np.uint8)
+    q_b = None
+    for (fi, uc, fl, pose) in frames:
+        nu_b, q = b.integrate(fi, uc, pose, cam, ids, fl, nu_b)
+        q_b = q if q_b is None else q_b
+    assert np.array_equal(nu_a, nu_b)
+    assert np.array_equal(q_a.view(np.uint32), q_b.view(np.uint32))
+    sa, wa, ca = a.download_chunks(ids)
+    sb, wb, cb = b.download_chunks(ids)
+    assert np.array_equal(sa.view(np.uint32), sb.view(np.uint32))
+    assert np.array_equal(wa.view(np.uint32), wb.view(np.uint32))
+    assert np.array_equal(ca, cb)
+
+
+def test_errors_and_edge_cases():
+    res = 0.02
+    seq = room_sequence(2)
+    cam = seq.cam
+    g = capi.Map(res)
+    fr = seq.frames[0]
+    with pytest.raises(capi.TexFusionError) as e:
+        g.prepare(123, fr.pose, cam)  # unknown frame
+    assert e.value.code == capi.TF_ERR_NOT_FOUND
+    g.upload_frame(fr.index, fr.depth)
+    # unknown chunk in an integrate list -> NOT_FOUND (reference: unordered_map::at throws)
+    with pytest.raises(capi.TexFusionError) as e:
+        g.integrate(fr.index, False, fr.pose, cam, np.array([[1000, 1000, 1000]], np.int32), 1)
+    assert e.value.code == capi.TF_ERR_NOT_FOUND
+    # empty list is a no-op (Structure/Chisel.h:228)
+    nu, q = g.integrate(fr.index, False, fr.pose, cam, np.zeros((0, 3), np.int32), 1)
+    assert len(nu) == 0
+    # all-invalid depth: bbox collapses to the 0.2 m shell around the camera, nothing is hit
+    g.upload_frame(7, np.zeros_like(fr.depth))
+    ids, new = g.prepare(7, fr.pose, cam)
+    o = OracleMap(res)
+    oi, _ = o.prepare(np.zeros_like(fr.depth), fr.pose, cam)
+    assert np.array_equal(ids, oi)
+    # colour requested but the frame has no colour plane
+    with pytest.raises(capi.TexFusionError):
+        g.integrate_frame(fr.index, True, fr.pose, cam)
+    # remove + has_chunk
+    ids, new = g.prepare(fr.index, fr.pose, cam)
+    assert g.has_chunk(ids[0]) and g.chunk_count() == len(ids)
+    g.remove_chunks(ids[:5])
+    assert not g.has_chunk(ids[0]) and g.chunk_count() == len(ids) - 5
+    g.remove_chunks(ids[:5])  # removing again is a no-op (RemoveChunk returns false)
+    assert g.chunk_count() == len(ids) - 5
+    g.reset()
+    assert g.chunk_count() == 0

@@ -1,0 +1,42 @@
+"""Shared helpers for the parity tests."""
+import functools
+
+import numpy as np
+
+from texturefusion_b200 import synth
+
+RESOLUTIONS = (0.04, 0.02, 0.01, 0.005)
+
+
+@functools.lru_cache(maxsize=8)
+def room_sequence(n_frames=6, start=0, total=300, scale=1.0, keyframe_every=3, noise=0.0):
+    cam = synth.Camera()
+    if scale != 1.0:
+        cam = cam.scaled(scale)
+    return synth.make_sequence(n_frames, cam=cam, total=total, keyframe_every=keyframe_every, start=start,
+                               noise_sigma=noise)
+
+
+def sort_ids(ids):
+    ids = np.asarray(ids, np.int32).reshape(-1, 3)
+    order = np.lexsort((ids[:, 2], ids[:, 1], ids[:, 0]))
+    return ids[order], order
+
+
+def assert_maps_equal(gpu_map, oracle_map, trunc_tol=True, what=""):
+    """Allocated-chunk set bit-exact; weights and colours bit-exact; TSDF within 1e-5 of the
+    truncation distance (north_star tolerance) — and report whether it is in fact bit-exact."""
+    gi, _ = sort_ids(gpu_map.list_chunks())
+    oi, _ = sort_ids(oracle_map.list_chunks())
+    assert gi.shape == oi.shape, f"{what}: chunk count {len(gi)} vs oracle {len(oi)}"
+    assert np.array_equal(gi, oi), f"{what}: allocated chunk sets differ"
+    if len(gi) == 0:
+        return True
+    gs, gw, gc = gpu_map.download_chunks(gi)
+    os_, ow, oc = oracle_map.download_chunks(oi)
+    assert np.array_equal(gw.view(np.uint32), ow.view(np.uint32)), f"{what}: weights not bit-exact"
+    assert np.array_equal(gc, oc), f"{what}: colour voxels differ"
+    # smallest truncation distance in use is at z ~ 0: (0.001504)*6
+    tol = 1e-5 * 0.009
+    assert np.all(np.abs(gs - os_) <= tol), f"{what}: sdf differs by {np.abs(gs - os_).max()}"
+    return bool(np.array_equal(gs.view(np.uint32), os_.view(np.uint32)))

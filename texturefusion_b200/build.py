@@ -1,0 +1,50 @@
+"""Builds libtexfusion_b200.so (sm_100a only) in-tree with nvcc."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG, "csrc")
+LIB_PATH = os.path.join(_PKG, "libtexfusion_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",  # the reference is un-fused AVX2 (no -mfma): keep every float op separately rounded
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall",
+    "-shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def sources() -> list[str]:
+    return [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC))] + [
+        os.path.join(os.path.dirname(_PKG), "include", "texfusion.h")]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in sources())
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if force or needs_build():
+        cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(_CSRC, "tf_capi.cu")]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force=True, verbose=True))

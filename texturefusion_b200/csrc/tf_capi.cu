@@ -1,0 +1,897 @@
+// tf_capi.cu — host runtime + C ABI (include/texfusion.h) of libtexfusion_b200.so.
+//
+// One tf_map = one GPU's share of the volumetric map: a device-resident open-addressing
+// hash (chunk id -> slot), an 8 KiB-per-chunk slab pool, a frame store (depth / RGBA /
+// quality / rgb planes kept in HBM), per-frame scratch lists and the texture atlas.
+// Every stage of a frame runs as a chain of kernels on one stream with device-side work
+// counts; the host synchronises once per call, when it needs the results.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/texfusion.h"
+#include "tf_host_math.h"
+#include "tf_kernels.cuh"
+
+using namespace tfb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct FrameSlot {
+  int frame_index = -1;
+  bool has_rgba = false, has_quality = false, has_rgb = false;
+  uint64_t last_use = 0;
+  float* depth = nullptr;
+  uchar4* rgba = nullptr;
+  float* quality = nullptr;
+  unsigned char* rgb = nullptr;
+  unsigned char* valid = nullptr;
+};
+
+struct EventPair {
+  cudaEvent_t a, b;
+  double bytes;
+};
+
+}  // namespace
+
+struct tf_map {
+  tf_config cfg;
+  int W = 0, H = 0, npix = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 0, grid = 0, grid_integrate = 0;
+
+  MapDev md{};
+  FrameState* fs = nullptr;
+  int hash_cap = 0;
+
+  // per-frame scratch
+  int cand_cap = 0, fine_words_cap = 0, list_cap = 0;
+  unsigned* words_c = nullptr;
+  int* coarse_list = nullptr;
+  unsigned* words_f = nullptr;
+  int* word_off = nullptr;
+  float* partial = nullptr;
+  int3* list_ids = nullptr;
+  int* list_slots = nullptr;
+  unsigned char* list_new = nullptr;
+  unsigned* list_upd = nullptr;
+  float* list_q = nullptr;
+
+  // mapped pinned result + output staging
+  FrameResultHost* res_h = nullptr;
+  FrameResultHost* res_d = nullptr;
+  int3* out_ids_h = nullptr;
+  unsigned char* out_new_h = nullptr;
+  unsigned char* out_upd_h = nullptr;
+  float* out_q_h = nullptr;
+  int3* out_ids_d = nullptr;
+  unsigned char* out_new_d = nullptr;
+  unsigned char* out_upd_d = nullptr;
+  float* out_q_d = nullptr;
+  unsigned* upd_stage_h = nullptr;  // pinned, list_cap
+  float* q_stage_h = nullptr;
+
+  // frame store
+  std::vector<FrameSlot> slots;
+  std::unordered_map<int, int> frame_to_slot;
+  uint64_t use_clock = 0;
+
+  // download staging
+  int dl_cap = 0;
+  float* dl_sdf = nullptr;
+  float* dl_w = nullptr;
+  uint2* dl_col = nullptr;
+  int* count_d = nullptr;
+
+  // atlas
+  unsigned char* atlas = nullptr;
+  uint64_t loc_next = 0;
+  int patch_w = 0, patch_h = 0;
+  std::unordered_map<unsigned long long, uint64_t> patches;
+  PatchDev* patch_d = nullptr;
+  int patch_cap = 0;
+
+  // host mirrors
+  int64_t n_live = 0;
+  int pool_next = 0;
+  tf_counters counters{};
+
+  // profiling of the integrate kernel
+  bool prof = false;
+  std::vector<EventPair> ev_pool, ev_pending;
+  double prof_ms = 0, prof_bytes = 0;
+  int64_t prof_launches = 0;
+};
+
+namespace {
+
+#define CUDA_OK(m, call)                                                                       \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      (m)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+      return TF_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+int fail(tf_map* m, int code, const std::string& msg) {
+  if (m) m->err = msg;
+  return code;
+}
+
+template <class T>
+cudaError_t dmalloc(T** p, size_t n) {
+  return cudaMalloc((void**)p, n * sizeof(T));
+}
+
+int check_kernel(tf_map* m, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(m, TF_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  m->counters.kernel_launches++;
+  return TF_OK;
+}
+
+bool cam_ok(const tf_map* m, const tf_camera* c) { return c && c->width == m->W && c->height == m->H; }
+
+int find_slot(tf_map* m, int32_t frame_index) {
+  auto it = m->frame_to_slot.find(frame_index);
+  if (it == m->frame_to_slot.end()) return -1;
+  m->slots[it->second].last_use = ++m->use_clock;
+  return it->second;
+}
+
+// Slot for frame_index: existing, free, or the least-recently-used one.
+int acquire_slot(tf_map* m, int32_t frame_index) {
+  int s = find_slot(m, frame_index);
+  if (s >= 0) return s;
+  int best = -1;
+  for (int i = 0; i < (int)m->slots.size(); i++) {
+    if (m->slots[i].frame_index < 0) { best = i; break; }
+    if (best < 0 || m->slots[i].last_use < m->slots[best].last_use) best = i;
+  }
+  FrameSlot& fsl = m->slots[best];
+  if (fsl.frame_index >= 0) m->frame_to_slot.erase(fsl.frame_index);
+  fsl.frame_index = frame_index;
+  fsl.has_rgba = fsl.has_quality = fsl.has_rgb = false;
+  fsl.last_use = ++m->use_clock;
+  m->frame_to_slot[frame_index] = best;
+  return best;
+}
+
+int ensure_color_planes(tf_map* m, FrameSlot& s) {
+  if (!s.rgba) {
+    CUDA_OK(m, dmalloc(&s.rgba, (size_t)m->npix));
+    CUDA_OK(m, dmalloc(&s.quality, (size_t)m->npix));
+    CUDA_OK(m, dmalloc(&s.rgb, (size_t)m->npix * 3));
+    CUDA_OK(m, dmalloc(&s.valid, (size_t)m->npix));
+  }
+  return TF_OK;
+}
+
+int dev_error_to_code(tf_map* m, int e) {
+  if (!e) return TF_OK;
+  cudaMemsetAsync(&m->fs->error, 0, sizeof(int), m->stream);
+  if (e & kErrMissing) return fail(m, TF_ERR_NOT_FOUND, "chunk id not in the map");
+  if (e & kErrCoord) return fail(m, TF_ERR_INVALID, "chunk coordinates outside +-2^20");
+  if (e & kErrPool) return fail(m, TF_ERR_CAPACITY, "chunk pool exhausted (raise tf_config.max_chunks)");
+  if (e & kErrList) return fail(m, TF_ERR_CAPACITY, "frame chunk list exceeds the list capacity");
+  return fail(m, TF_ERR_CAPACITY, "culling candidate grid exceeds capacity");
+}
+
+void absorb_result(tf_map* m) {
+  m->n_live = m->res_h->n_live;
+  m->pool_next = m->res_h->pool_next;
+  m->counters.pool_used = m->n_live;
+}
+
+// ---- profiling helpers ---------------------------------------------------------------------
+void prof_begin(tf_map* m, EventPair& ep) {
+  if (m->ev_pool.empty()) {
+    cudaEventCreate(&ep.a);
+    cudaEventCreate(&ep.b);
+  } else {
+    ep = m->ev_pool.back();
+    m->ev_pool.pop_back();
+  }
+  cudaEventRecord(ep.a, m->stream);
+}
+void prof_end(tf_map* m, EventPair& ep) {
+  cudaEventRecord(ep.b, m->stream);
+  ep.bytes = -1;
+  m->ev_pending.push_back(ep);
+}
+// after a stream sync: fold finished event pairs; `bytes` = algorithmic bytes of the launch
+void prof_collect(tf_map* m, double bytes_last) {
+  for (size_t i = 0; i < m->ev_pending.size(); i++) {
+    EventPair& ep = m->ev_pending[i];
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) {
+      m->prof_ms += ms;
+      m->prof_launches++;
+      m->prof_bytes += (ep.bytes >= 0 ? ep.bytes : bytes_last);
+    }
+    m->ev_pool.push_back(ep);
+  }
+  m->ev_pending.clear();
+}
+
+// algorithmic bytes of one integrate launch: 16 B per visited voxel for a
+// depth-only frame, 32 B with colour, plus the image planes once per frame.
+double algorithmic_bytes(const tf_map* m, int64_t n_chunks, const bool* color, int n_frames) {
+  double b = 0;
+  for (int f = 0; f < n_frames; f++)
+    b += (double)n_chunks * 512.0 * (color[f] ? 32.0 : 16.0) + (double)m->npix * (color[f] ? 12.0 : 4.0);
+  return b;
+}
+
+// ---- pipeline stages -------------------------------------------------------------------------
+
+int launch_cull(tf_map* m, const CullParams& cp, const float* depth, int do_alloc) {
+  bbox_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->partial, m->cand_cap);
+  if (int rc = check_kernel(m, "bbox_kernel")) return rc;
+  cull_coarse_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->words_c, m->coarse_list,
+                                                          m->fine_words_cap);
+  if (int rc = check_kernel(m, "cull_coarse_kernel")) return rc;
+  cull_fine_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->coarse_list, m->words_f, m->word_off,
+                                                        m->cfg.n_ranks, m->cfg.rank, m->list_cap);
+  if (int rc = check_kernel(m, "cull_fine_kernel")) return rc;
+  if (do_alloc >= 0) {
+    alloc_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, m->md, m->fs, m->coarse_list, m->words_f, m->word_off,
+                                                      m->list_ids, m->list_slots, m->list_new, do_alloc);
+    if (int rc = check_kernel(m, "alloc_kernel")) return rc;
+  }
+  return TF_OK;
+}
+
+int launch_integrate(tf_map* m, const GroupParams& gp, const int* n_dev, int n_host, double bytes) {
+  EventPair ep;
+  if (m->prof) prof_begin(m, ep);
+  integrate_kernel<<<m->grid_integrate, kThreads, 0, m->stream>>>(gp, m->md, m->list_slots, n_dev, n_host,
+                                                                  m->list_upd, m->list_q);
+  if (m->prof) {
+    prof_end(m, ep);
+    m->ev_pending.back().bytes = bytes;
+  }
+  return check_kernel(m, "integrate_kernel");
+}
+
+int build_group(tf_map* m, const tf_group_frame* frames, int n_frames, const tf_camera* cam, GroupParams& gp,
+                bool* color_flags) {
+  if (n_frames < 1 || n_frames > kMaxGroupFrames) return fail(m, TF_ERR_INVALID, "group size must be 1..8");
+  make_group_consts(m->cfg.voxel_res, m->cfg.trunc, gp);
+  gp.n_frames = n_frames;
+  for (int f = 0; f < n_frames; f++) {
+    const int s = find_slot(m, frames[f].frame_index);
+    if (s < 0) return fail(m, TF_ERR_NOT_FOUND, "frame_index not in the frame store");
+    const FrameSlot& fsl = m->slots[s];
+    const bool color = frames[f].use_color != 0;
+    if (color && !m->cfg.use_color) return fail(m, TF_ERR_INVALID, "map created with use_color = 0");
+    if (color && !fsl.has_rgba) return fail(m, TF_ERR_NOT_FOUND, "frame has no colour plane");
+    make_frame_dev(frames[f].pose, *cam, frames[f].flag, fsl.depth, color ? fsl.rgba : nullptr,
+                   (color && fsl.has_quality) ? fsl.quality : nullptr, gp.f[f]);
+    color_flags[f] = color;
+  }
+  return TF_OK;
+}
+
+int upload_ids(tf_map* m, const tf_chunk_id* ids, int64_t n) {
+  if (n > m->list_cap) return fail(m, TF_ERR_CAPACITY, "chunk list exceeds the list capacity");
+  CUDA_OK(m, cudaMemcpyAsync(m->list_ids, ids, (size_t)n * sizeof(int3), cudaMemcpyHostToDevice, m->stream));
+  m->counters.h2d_bytes += n * (int64_t)sizeof(int3);
+  return TF_OK;
+}
+
+// ids (host) -> list_slots (device); fails with TF_ERR_NOT_FOUND before anything is modified.
+int lookup_ids(tf_map* m, const tf_chunk_id* ids, int64_t n, bool must_exist) {
+  if (int rc = upload_ids(m, ids, n)) return rc;
+  const int grid = (int)std::min<int64_t>(m->grid, (n + kThreads - 1) / kThreads);
+  lookup_kernel<<<std::max(grid, 1), kThreads, 0, m->stream>>>(m->md, m->fs, m->list_ids, (int)n, m->list_slots);
+  if (int rc = check_kernel(m, "lookup_kernel")) return rc;
+  publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);
+  if (int rc = check_kernel(m, "publish_kernel")) return rc;
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  const int e = m->res_h->error;
+  if (e) {
+    cudaMemsetAsync(&m->fs->error, 0, sizeof(int), m->stream);
+    if (must_exist || (e & ~kErrMissing)) return dev_error_to_code(m, e);
+  }
+  return TF_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+const char* tf_last_error(const tf_map* m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+
+void* tf_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void tf_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+void tf_destroy(tf_map* m) {
+  if (!m) return;
+  cudaSetDevice(m->cfg.device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  cudaFree(m->md.keys); cudaFree(m->md.vals); cudaFree(m->md.pool); cudaFree(m->md.slot_id);
+  cudaFree(m->md.slot_flags); cudaFree(m->md.free_stack); cudaFree(m->fs);
+  cudaFree(m->words_c); cudaFree(m->coarse_list); cudaFree(m->words_f); cudaFree(m->word_off);
+  cudaFree(m->partial); cudaFree(m->list_ids); cudaFree(m->list_slots); cudaFree(m->list_new);
+  cudaFree(m->list_upd); cudaFree(m->list_q); cudaFree(m->dl_sdf); cudaFree(m->dl_w); cudaFree(m->dl_col);
+  cudaFree(m->count_d); cudaFree(m->atlas); cudaFree(m->patch_d);
+  cudaFreeHost(m->res_h); cudaFreeHost(m->out_ids_h); cudaFreeHost(m->out_new_h); cudaFreeHost(m->out_upd_h);
+  cudaFreeHost(m->out_q_h); cudaFreeHost(m->upd_stage_h); cudaFreeHost(m->q_stage_h);
+  for (auto& s : m->slots) {
+    cudaFree(s.depth); cudaFree(s.rgba); cudaFree(s.quality); cudaFree(s.rgb); cudaFree(s.valid);
+  }
+  for (auto& ep : m->ev_pool) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
+  for (auto& ep : m->ev_pending) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+static int reset_device_state(tf_map* m) {
+  CUDA_OK(m, cudaMemsetAsync(m->md.keys, 0xFF, (size_t)m->hash_cap * sizeof(unsigned long long), m->stream));
+  CUDA_OK(m, cudaMemsetAsync(m->md.slot_flags, 0, (size_t)m->md.max_chunks, m->stream));
+  CUDA_OK(m, cudaMemsetAsync(m->fs, 0, sizeof(FrameState), m->stream));
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  m->n_live = 0;
+  m->pool_next = 0;
+  return TF_OK;
+}
+
+int tf_create(tf_map** out, const tf_config* cfg) {
+  if (!out || !cfg) { g_create_error = "null argument"; return TF_ERR_INVALID; }
+  *out = nullptr;
+  if (cfg->chunk_dim != 8) { g_create_error = "chunk_dim must be 8"; return TF_ERR_INVALID; }
+  if (!(cfg->voxel_res > 0)) { g_create_error = "voxel_res must be positive"; return TF_ERR_INVALID; }
+  if (cfg->n_ranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->n_ranks) {
+    g_create_error = "bad n_ranks/rank";
+    return TF_ERR_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e);
+    return TF_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "bad device ordinal"; return TF_ERR_INVALID; }
+  tf_map* m = new tf_map;
+  m->cfg = *cfg;
+  m->W = cfg->width > 0 ? cfg->width : 640;
+  m->H = cfg->height > 0 ? cfg->height : 480;
+  m->npix = m->W * m->H;
+  if (m->W % 8 != 0) {  // the reference's bbox loop consumes 8 pixels per step (ChunkManager.h:326-328)
+    g_create_error = "frame width must be a multiple of 8";
+    delete m;
+    return TF_ERR_INVALID;
+  }
+  auto bail = [&](int rc) {
+    g_create_error = m->err;
+    tf_destroy(m);
+    return rc;
+  };
+#define C_OK(call)                                                                   \
+  do {                                                                               \
+    cudaError_t e_ = (call);                                                         \
+    if (e_ != cudaSuccess) {                                                         \
+      m->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+      return bail(TF_ERR_CUDA);                                                      \
+    }                                                                                \
+  } while (0)
+  C_OK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  C_OK(cudaGetDeviceProperties(&prop, cfg->device));
+  m->sm_count = prop.multiProcessorCount;
+  C_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  int occ = 1;
+  C_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, integrate_kernel, kThreads, 0));
+  m->grid = m->sm_count * 2;
+  m->grid_integrate = m->sm_count * std::max(1, occ);
+
+  const int64_t max_chunks = cfg->max_chunks > 0 ? cfg->max_chunks : (int64_t)1 << 19;
+  if (max_chunks > ((int64_t)1 << 27)) { m->err = "max_chunks too large"; return bail(TF_ERR_INVALID); }
+  m->md.max_chunks = (int)max_chunks;
+  int hc = 1024;
+  while (hc < 2 * max_chunks) hc <<= 1;
+  m->hash_cap = hc;
+  m->md.hash_mask = (unsigned)hc - 1;
+  m->md.n_ranks = cfg->n_ranks;
+  m->md.rank = cfg->rank;
+  C_OK(dmalloc(&m->md.keys, (size_t)hc));
+  C_OK(dmalloc(&m->md.vals, (size_t)hc));
+  C_OK(cudaMalloc((void**)&m->md.pool, (size_t)max_chunks * kChunkBytes));
+  C_OK(dmalloc(&m->md.slot_id, (size_t)max_chunks));
+  C_OK(dmalloc(&m->md.slot_flags, (size_t)max_chunks));
+  C_OK(dmalloc(&m->md.free_stack, (size_t)max_chunks));
+  C_OK(dmalloc(&m->fs, 1));
+
+  m->cand_cap = 1 << 23;
+  m->fine_words_cap = 1 << 20;
+  m->list_cap = 1 << 19;
+  C_OK(dmalloc(&m->words_c, (size_t)m->cand_cap / 32));
+  C_OK(dmalloc(&m->coarse_list, (size_t)m->cand_cap));
+  C_OK(dmalloc(&m->words_f, (size_t)m->fine_words_cap));
+  C_OK(dmalloc(&m->word_off, (size_t)m->fine_words_cap));
+  C_OK(dmalloc(&m->partial, (size_t)m->grid * 6));
+  C_OK(dmalloc(&m->list_ids, (size_t)m->list_cap));
+  C_OK(dmalloc(&m->list_slots, (size_t)m->list_cap));
+  C_OK(dmalloc(&m->list_new, (size_t)m->list_cap));
+  C_OK(dmalloc(&m->list_upd, (size_t)m->list_cap));
+  C_OK(dmalloc(&m->list_q, (size_t)m->list_cap));
+  C_OK(dmalloc(&m->count_d, 1));
+
+  const unsigned hflags = cudaHostAllocMapped;
+  C_OK(cudaHostAlloc((void**)&m->res_h, sizeof(FrameResultHost), hflags));
+  C_OK(cudaHostAlloc((void**)&m->out_ids_h, (size_t)m->list_cap * sizeof(int3), hflags));
+  C_OK(cudaHostAlloc((void**)&m->out_new_h, (size_t)m->list_cap, hflags));
+  C_OK(cudaHostAlloc((void**)&m->out_upd_h, (size_t)m->list_cap, hflags));
+  C_OK(cudaHostAlloc((void**)&m->out_q_h, (size_t)m->list_cap * sizeof(float), hflags));
+  C_OK(cudaHostAlloc((void**)&m->upd_stage_h, (size_t)m->list_cap * sizeof(unsigned), cudaHostAllocDefault));
+  C_OK(cudaHostAlloc((void**)&m->q_stage_h, (size_t)m->list_cap * sizeof(float), cudaHostAllocDefault));
+  memset(m->res_h, 0, sizeof(FrameResultHost));
+  C_OK(cudaHostGetDevicePointer((void**)&m->res_d, m->res_h, 0));
+  C_OK(cudaHostGetDevicePointer((void**)&m->out_ids_d, m->out_ids_h, 0));
+  C_OK(cudaHostGetDevicePointer((void**)&m->out_new_d, m->out_new_h, 0));
+  C_OK(cudaHostGetDevicePointer((void**)&m->out_upd_d, m->out_upd_h, 0));
+  C_OK(cudaHostGetDevicePointer((void**)&m->out_q_d, m->out_q_h, 0));
+
+  const int max_frames = cfg->max_frames > 0 ? cfg->max_frames : 32;
+  m->slots.resize(max_frames);
+  for (auto& s : m->slots) C_OK(dmalloc(&s.depth, (size_t)m->npix));
+
+  // Atlas::SetResolution (Structure/Atlas.h:62-65)
+  m->patch_w = (int)std::floor(4800 * cfg->voxel_res);
+  m->patch_h = (int)std::floor(3600 * cfg->voxel_res);
+#undef C_OK
+  if (int rc = reset_device_state(m)) return bail(rc);
+  m->counters.pool_capacity = max_chunks;
+  *out = m;
+  return TF_OK;
+}
+
+int tf_reset(tf_map* m) {
+  if (!m) return TF_ERR_INVALID;
+  cudaSetDevice(m->cfg.device);
+  return reset_device_state(m);
+}
+
+int tf_sync(tf_map* m) {
+  if (!m) return TF_ERR_INVALID;
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  prof_collect(m, 0);
+  return TF_OK;
+}
+
+void* tf_stream(tf_map* m) { return m ? (void*)m->stream : nullptr; }
+
+// ---- frame store ---------------------------------------------------------------------------
+
+int tf_upload_frame(tf_map* m, int32_t frame_index, const float* depth, const uint8_t* rgba,
+                    const float* quality) {
+  if (!m || !depth || frame_index < 0) return fail(m, TF_ERR_INVALID, "tf_upload_frame: bad argument");
+  const int s = acquire_slot(m, frame_index);
+  FrameSlot& fsl = m->slots[s];
+  const size_t nb = (size_t)m->npix * 4;
+  CUDA_OK(m, cudaMemcpyAsync(fsl.depth, depth, nb, cudaMemcpyHostToDevice, m->stream));
+  m->counters.h2d_bytes += nb;
+  if (rgba || quality) {
+    if (int rc = ensure_color_planes(m, fsl)) return rc;
+  }
+  if (rgba) {
+    CUDA_OK(m, cudaMemcpyAsync(fsl.rgba, rgba, nb, cudaMemcpyHostToDevice, m->stream));
+    m->counters.h2d_bytes += nb;
+    fsl.has_rgba = true;
+  }
+  if (quality) {
+    CUDA_OK(m, cudaMemcpyAsync(fsl.quality, quality, nb, cudaMemcpyHostToDevice, m->stream));
+    m->counters.h2d_bytes += nb;
+    fsl.has_quality = true;
+  }
+  return TF_OK;
+}
+
+int tf_upload_keyframe_rgb(tf_map* m, int32_t frame_index, const uint8_t* rgb, const uint8_t* color_valid) {
+  if (!m || !rgb) return fail(m, TF_ERR_INVALID, "tf_upload_keyframe_rgb: bad argument");
+  const int s = find_slot(m, frame_index);
+  if (s < 0) return fail(m, TF_ERR_NOT_FOUND, "frame_index not in the frame store (upload depth first)");
+  FrameSlot& fsl = m->slots[s];
+  if (int rc = ensure_color_planes(m, fsl)) return rc;
+  CUDA_OK(m, cudaMemcpyAsync(fsl.rgb, rgb, (size_t)m->npix * 3, cudaMemcpyHostToDevice, m->stream));
+  m->counters.h2d_bytes += (int64_t)m->npix * 3;
+  if (color_valid) {
+    CUDA_OK(m, cudaMemcpyAsync(fsl.valid, color_valid, (size_t)m->npix, cudaMemcpyHostToDevice, m->stream));
+    m->counters.h2d_bytes += m->npix;
+  }
+  pack_rgba_kernel<<<m->grid, kThreads, 0, m->stream>>>(fsl.rgb, color_valid ? fsl.valid : nullptr, fsl.rgba, m->npix);
+  if (int rc = check_kernel(m, "pack_rgba_kernel")) return rc;
+  fsl.has_rgb = true;
+  fsl.has_rgba = true;
+  return TF_OK;
+}
+
+int tf_release_frame(tf_map* m, int32_t frame_index) {
+  if (!m) return TF_ERR_INVALID;
+  auto it = m->frame_to_slot.find(frame_index);
+  if (it == m->frame_to_slot.end()) return fail(m, TF_ERR_NOT_FOUND, "frame_index not in the frame store");
+  m->slots[it->second].frame_index = -1;
+  m->frame_to_slot.erase(it);
+  return TF_OK;
+}
+
+int tf_frame_device_ptrs(tf_map* m, int32_t frame_index, int has_color, void** depth, void** rgba,
+                         void** quality) {
+  if (!m || frame_index < 0) return fail(m, TF_ERR_INVALID, "tf_frame_device_ptrs: bad argument");
+  const int s = acquire_slot(m, frame_index);
+  FrameSlot& fsl = m->slots[s];
+  if (has_color) {
+    if (int rc = ensure_color_planes(m, fsl)) return rc;
+    fsl.has_rgba = fsl.has_quality = true;
+  }
+  if (depth) *depth = fsl.depth;
+  if (rgba) *rgba = has_color ? (void*)fsl.rgba : nullptr;
+  if (quality) *quality = has_color ? (void*)fsl.quality : nullptr;
+  return TF_OK;
+}
+
+// ---- prepare / integrate / finalize --------------------------------------------------------
+
+int tf_prepare(tf_map* m, int32_t frame_index, const tf_pose* pose, const tf_camera* cam, tf_chunk_id* ids_out,
+               uint8_t* is_new_out, int64_t cap, int64_t* n_out) {
+  if (!m || !pose || !n_out || !cam_ok(m, cam)) return fail(m, TF_ERR_INVALID, "tf_prepare: bad argument");
+  const int s = find_slot(m, frame_index);
+  if (s < 0) return fail(m, TF_ERR_NOT_FOUND, "frame_index not in the frame store");
+  CullParams cp;
+  make_cull_params(m->cfg.voxel_res, m->cfg.trunc, *pose, *cam, cp);
+  // pass 1: culling only, to learn the list length before anything is created
+  if (int rc = launch_cull(m, cp, m->slots[s].depth, -1)) return rc;
+  publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);
+  if (int rc = check_kernel(m, "publish_kernel")) return rc;
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  if (int rc = dev_error_to_code(m, m->res_h->error)) return rc;
+  const int64_t n = m->res_h->n_chunks;
+  *n_out = n;
+  if (n > cap || (n > 0 && (!ids_out || !is_new_out)))
+    return fail(m, TF_ERR_CAPACITY, "tf_prepare: output capacity too small");
+  // pass 2: HasChunk / CreateChunk
+  alloc_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, m->md, m->fs, m->coarse_list, m->words_f, m->word_off,
+                                                    m->list_ids, m->list_slots, m->list_new, 1);
+  if (int rc = check_kernel(m, "alloc_kernel")) return rc;
+  publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);
+  if (int rc = check_kernel(m, "publish_kernel")) return rc;
+  if (n > 0) {
+    CUDA_OK(m, cudaMemcpyAsync(ids_out, m->list_ids, (size_t)n * sizeof(int3), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(m, cudaMemcpyAsync(is_new_out, m->list_new, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    m->counters.d2h_bytes += n * 13;
+  }
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  absorb_result(m);
+  return dev_error_to_code(m, m->res_h->error);
+}
+
+int tf_integrate_group(tf_map* m, const tf_group_frame* frames, int32_t n_frames, const tf_camera* cam,
+                       const tf_chunk_id* ids, int64_t n, uint8_t* needs_update, float* quality_out) {
+  if (!m || !frames || !cam_ok(m, cam) || n < 0 || (n > 0 && (!ids || !needs_update)))
+    return fail(m, TF_ERR_INVALID, "tf_integrate_group: bad argument");
+  GroupParams gp;
+  bool color[kMaxGroupFrames];
+  if (int rc = build_group(m, frames, n_frames, cam, gp, color)) return rc;
+  if (n == 0) return TF_OK;  // Structure/Chisel.h:228
+  if (int rc = lookup_ids(m, ids, n, true)) return rc;
+  if (int rc = launch_integrate(m, gp, nullptr, (int)n, algorithmic_bytes(m, n, color, n_frames))) return rc;
+  CUDA_OK(m, cudaMemcpyAsync(m->upd_stage_h, m->list_upd, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, m->stream));
+  if (quality_out)
+    CUDA_OK(m, cudaMemcpyAsync(m->q_stage_h, m->list_q, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  prof_collect(m, 0);
+  m->counters.d2h_bytes += n * (quality_out ? 8 : 4);
+  for (int64_t i = 0; i < n; i++) needs_update[i] = (needs_update[i] || m->upd_stage_h[i] != 0) ? 1 : 0;
+  if (quality_out) memcpy(quality_out, m->q_stage_h, (size_t)n * sizeof(float));
+  m->counters.frames_integrated += n_frames;
+  m->counters.voxel_updates += n * 512 * n_frames;
+  return TF_OK;
+}
+
+int tf_integrate(tf_map* m, int32_t frame_index, int use_color, const tf_pose* pose, const tf_camera* cam,
+                 const tf_chunk_id* ids, int64_t n, int flag, uint8_t* needs_update, float* quality_out) {
+  if (!m || !pose) return fail(m, TF_ERR_INVALID, "tf_integrate: bad argument");
+  tf_group_frame g;
+  g.frame_index = frame_index;
+  g.use_color = use_color;
+  g.flag = flag;
+  g.reserved = 0;
+  g.pose = *pose;
+  return tf_integrate_group(m, &g, 1, cam, ids, n, needs_update, quality_out);
+}
+
+int tf_remove_chunks(tf_map* m, const tf_chunk_id* ids, int64_t n) {
+  if (!m || n < 0 || (n > 0 && !ids)) return fail(m, TF_ERR_INVALID, "tf_remove_chunks: bad argument");
+  if (n == 0) return TF_OK;
+  if (int rc = upload_ids(m, ids, n)) return rc;
+  const int grid = (int)std::min<int64_t>(m->grid, (n + kThreads - 1) / kThreads);
+  remove_kernel<<<std::max(grid, 1), kThreads, 0, m->stream>>>(m->md, m->fs, m->list_ids, (int)n);
+  if (int rc = check_kernel(m, "remove_kernel")) return rc;
+  publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);
+  if (int rc = check_kernel(m, "publish_kernel")) return rc;
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  absorb_result(m);
+  return TF_OK;
+}
+
+// Shared tail of the fused pipelines: prepare on frames[0], integrate the group, finalize.
+static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, const tf_camera* cam,
+                       tf_frame_stats* stats, tf_chunk_id* ids_out, uint8_t* new_out, uint8_t* upd_out,
+                       float* q_out, int64_t cap) {
+  GroupParams gp;
+  bool color[kMaxGroupFrames];
+  if (int rc = build_group(m, frames, n_frames, cam, gp, color)) return rc;
+  const int s = find_slot(m, frames[0].frame_index);
+  CullParams cp;
+  make_cull_params(m->cfg.voxel_res, m->cfg.trunc, frames[0].pose, *cam, cp);
+  if (int rc = launch_cull(m, cp, m->slots[s].depth, 1)) return rc;
+  if (int rc = launch_integrate(m, gp, &m->fs->n_list, 0, -1)) return rc;
+  const int ocap = (int)std::min<int64_t>(cap, m->list_cap);
+  finalize_kernel<<<m->grid, kThreads, 0, m->stream>>>(
+      m->md, m->fs, m->list_ids, m->list_slots, m->list_new, m->list_upd, m->list_q, 1,
+      ids_out ? m->out_ids_d : nullptr, new_out ? m->out_new_d : nullptr, upd_out ? m->out_upd_d : nullptr,
+      q_out ? m->out_q_d : nullptr, ocap, m->res_d);
+  if (int rc = check_kernel(m, "finalize_kernel")) return rc;
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  absorb_result(m);
+  const FrameResultHost r = *m->res_h;
+  prof_collect(m, algorithmic_bytes(m, r.n_chunks, color, n_frames));
+  const int64_t nout = std::min<int64_t>(r.n_chunks, ocap);
+  if (ids_out) memcpy(ids_out, m->out_ids_h, (size_t)nout * sizeof(int3));
+  if (new_out) memcpy(new_out, m->out_new_h, (size_t)nout);
+  if (upd_out) memcpy(upd_out, m->out_upd_h, (size_t)nout);
+  if (q_out) memcpy(q_out, m->out_q_h, (size_t)nout * sizeof(float));
+  m->counters.d2h_bytes += sizeof(FrameResultHost) + nout * ((ids_out ? 12 : 0) + (new_out ? 1 : 0) + (upd_out ? 1 : 0) + (q_out ? 4 : 0));
+  if (stats) {
+    stats->n_chunks = r.n_chunks;
+    stats->n_new = r.n_new;
+    stats->n_updated = r.n_updated;
+    stats->n_removed = r.n_removed;
+    stats->voxel_updates = (int64_t)r.n_chunks * 512 * n_frames;
+  }
+  m->counters.frames_integrated += n_frames;
+  m->counters.voxel_updates += (int64_t)r.n_chunks * 512 * n_frames;
+  return dev_error_to_code(m, r.error);
+}
+
+int tf_integrate_frame(tf_map* m, int32_t frame_index, int use_color, const tf_pose* pose, const tf_camera* cam,
+                       tf_frame_stats* stats, tf_chunk_id* ids_out, uint8_t* is_new_out, uint8_t* updated_out,
+                       float* quality_out, int64_t cap) {
+  if (!m || !pose || !cam_ok(m, cam) || cap < 0) return fail(m, TF_ERR_INVALID, "tf_integrate_frame: bad argument");
+  tf_group_frame g;
+  g.frame_index = frame_index;
+  g.use_color = use_color;
+  g.flag = 1;
+  g.reserved = 0;
+  g.pose = *pose;
+  return fused_group(m, &g, 1, cam, stats, ids_out, is_new_out, updated_out, quality_out, cap);
+}
+
+int tf_integrate_batch(tf_map* m, const tf_batch_item* items, int64_t n_items, const tf_camera* cam) {
+  if (!m || n_items < 0 || (n_items > 0 && !items) || !cam_ok(m, cam))
+    return fail(m, TF_ERR_INVALID, "tf_integrate_batch: bad argument");
+  std::vector<tf_chunk_id> ids;
+  std::vector<uint8_t> upd;
+  std::vector<float> q;
+  for (int64_t k = 0; k < n_items; k++) {
+    const tf_batch_item& it = items[k];
+    if (!it.frames || it.n_frames < 1) return fail(m, TF_ERR_INVALID, "tf_integrate_batch: empty item");
+    if (it.flag == 0) {
+      // de-integration over kf.validChunks (GCFusion/MobileFusion.cpp:135-143): flags start true
+      upd.assign((size_t)it.n_ids, 1);
+      std::vector<tf_group_frame> fr(it.frames, it.frames + it.n_frames);
+      for (auto& f : fr) f.flag = 0;
+      if (int rc = tf_integrate_group(m, fr.data(), it.n_frames, cam, it.ids, it.n_ids, upd.data(), nullptr)) return rc;
+    } else {
+      std::vector<tf_group_frame> fr(it.frames, it.frames + it.n_frames);
+      for (auto& f : fr) f.flag = 1;
+      ids.resize(m->list_cap);
+      upd.resize(m->list_cap);
+      q.resize(m->list_cap);
+      tf_frame_stats st;
+      if (int rc = fused_group(m, fr.data(), it.n_frames, cam, &st, ids.data(), nullptr, upd.data(), q.data(), m->list_cap))
+        return rc;
+      int64_t nv = 0;
+      for (int64_t i = 0; i < st.n_chunks; i++) {
+        if (!upd[i]) continue;
+        if (nv < it.cap) {
+          if (it.valid_out) it.valid_out[nv] = ids[i];
+          if (it.quality_out) it.quality_out[nv] = q[i];
+        }
+        nv++;
+      }
+      if (it.n_valid_out) *it.n_valid_out = nv;
+      if (nv > it.cap && it.valid_out) return fail(m, TF_ERR_CAPACITY, "tf_integrate_batch: valid_out too small");
+    }
+  }
+  return TF_OK;
+}
+
+// ---- queries ---------------------------------------------------------------------------------
+
+int tf_has_chunk(tf_map* m, tf_chunk_id id) {
+  if (!m) return TF_ERR_INVALID;
+  if (int rc = lookup_ids(m, &id, 1, false)) return rc;
+  int slot = -1;
+  CUDA_OK(m, cudaMemcpy(&slot, m->list_slots, sizeof(int), cudaMemcpyDeviceToHost));
+  return slot >= 0 ? 1 : 0;
+}
+
+int64_t tf_chunk_count(tf_map* m) { return m ? m->n_live : TF_ERR_INVALID; }
+
+int tf_list_chunks(tf_map* m, tf_chunk_id* out, int64_t cap, int64_t* n_out) {
+  if (!m || !n_out) return fail(m, TF_ERR_INVALID, "tf_list_chunks: bad argument");
+  *n_out = m->n_live;
+  if (m->n_live == 0) return TF_OK;
+  if (cap < m->n_live || !out) return fail(m, TF_ERR_CAPACITY, "tf_list_chunks: output capacity too small");
+  int3* tmp = nullptr;
+  CUDA_OK(m, dmalloc(&tmp, (size_t)m->n_live));
+  cudaMemsetAsync(m->count_d, 0, sizeof(int), m->stream);
+  list_kernel<<<m->grid, kThreads, 0, m->stream>>>(m->md, m->pool_next, tmp, (int)m->n_live, m->count_d);
+  int rc = check_kernel(m, "list_kernel");
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(out, tmp, (size_t)m->n_live * sizeof(int3), cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) rc = fail(m, TF_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaFree(tmp);
+  m->counters.d2h_bytes += m->n_live * 12;
+  return rc;
+}
+
+int tf_download_chunks(tf_map* m, const tf_chunk_id* ids, int64_t n, float* sdf, float* weight, uint16_t* color) {
+  if (!m || n < 0 || (n > 0 && !ids)) return fail(m, TF_ERR_INVALID, "tf_download_chunks: bad argument");
+  if (!m->dl_sdf) {
+    m->dl_cap = 8192;
+    CUDA_OK(m, dmalloc(&m->dl_sdf, (size_t)m->dl_cap * 512));
+    CUDA_OK(m, dmalloc(&m->dl_w, (size_t)m->dl_cap * 512));
+    CUDA_OK(m, dmalloc(&m->dl_col, (size_t)m->dl_cap * 512));
+  }
+  for (int64_t base = 0; base < n; base += m->dl_cap) {
+    const int64_t cnt = std::min<int64_t>(m->dl_cap, n - base);
+    if (int rc = lookup_ids(m, ids + base, cnt, true)) return rc;
+    const int grid = (int)std::min<int64_t>(m->grid * 4, (cnt + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    download_kernel<<<std::max(grid, 1), kThreads, 0, m->stream>>>(m->md, m->list_slots, (int)cnt, sdf ? m->dl_sdf : nullptr,
+                                                                   weight ? m->dl_w : nullptr, color ? m->dl_col : nullptr);
+    if (int rc = check_kernel(m, "download_kernel")) return rc;
+    if (sdf) CUDA_OK(m, cudaMemcpyAsync(sdf + base * 512, m->dl_sdf, (size_t)cnt * 2048, cudaMemcpyDeviceToHost, m->stream));
+    if (weight) CUDA_OK(m, cudaMemcpyAsync(weight + base * 512, m->dl_w, (size_t)cnt * 2048, cudaMemcpyDeviceToHost, m->stream));
+    if (color) CUDA_OK(m, cudaMemcpyAsync(color + base * 2048, m->dl_col, (size_t)cnt * 4096, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(m, cudaStreamSynchronize(m->stream));
+    m->counters.d2h_bytes += cnt * ((sdf ? 2048 : 0) + (weight ? 2048 : 0) + (color ? 4096 : 0));
+  }
+  return TF_OK;
+}
+
+// ---- atlas ---------------------------------------------------------------------------------------
+
+int tf_atlas_patch_size(tf_map* m, int32_t* w, int32_t* h) {
+  if (!m || !w || !h) return TF_ERR_INVALID;
+  *w = m->patch_w;
+  *h = m->patch_h;
+  return TF_OK;
+}
+
+int tf_atlas_alloc_slot(tf_map* m, tf_chunk_id id, uint64_t* texloc_out) {
+  if (!m || !texloc_out || !coord_ok(id.x, id.y, id.z)) return fail(m, TF_ERR_INVALID, "tf_atlas_alloc_slot: bad argument");
+  const unsigned long long key = pack_key(id.x, id.y, id.z);
+  auto it = m->patches.find(key);
+  if (it != m->patches.end()) {
+    *texloc_out = it->second;
+    return TF_OK;
+  }
+  // Atlas::AddPatch (Structure/Atlas.cpp:43-64)
+  const uint64_t loc = m->loc_next;
+  uint64_t x = loc % kAtlasDim, y = loc / kAtlasDim;
+  if (x >= (uint64_t)kAtlasDim || y >= (uint64_t)kAtlasDim)
+    return fail(m, TF_ERR_ATLAS_FULL, "No enough space for texture storage.");
+  if (x + m->patch_w >= (uint64_t)kAtlasDim) {
+    x = 0;
+    y += m->patch_h;
+  } else {
+    x += m->patch_w;
+  }
+  m->loc_next = x + y * kAtlasDim;
+  m->patches.emplace(key, loc);
+  *texloc_out = loc;
+  return TF_OK;
+}
+
+static int ensure_atlas(tf_map* m) {
+  if (m->atlas) return TF_OK;
+  const size_t bytes = (size_t)kAtlasDim * kAtlasDim * 3;
+  CUDA_OK(m, cudaMalloc((void**)&m->atlas, bytes));
+  CUDA_OK(m, cudaMemsetAsync(m->atlas, 0, bytes, m->stream));  // Structure/Atlas.cpp:35-36
+  return TF_OK;
+}
+
+int tf_atlas_update(tf_map* m, const tf_patch_desc* patches, int64_t n) {
+  if (!m || n < 0 || (n > 0 && !patches)) return fail(m, TF_ERR_INVALID, "tf_atlas_update: bad argument");
+  if (n == 0) return TF_OK;
+  if (int rc = ensure_atlas(m)) return rc;
+  std::vector<PatchDev> pd((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    const tf_patch_desc& p = patches[i];
+    const int s = find_slot(m, p.frame_index);
+    if (s < 0 || !m->slots[s].has_rgb) return fail(m, TF_ERR_NOT_FOUND, "tf_atlas_update: key-frame rgb not in the frame store");
+    if (p.w <= 0 || p.h <= 0 || p.x < 0 || p.y < 0 || p.x + p.w > m->W || p.y + p.h > m->H)
+      return fail(m, TF_ERR_INVALID, "tf_atlas_update: bbox outside the image");
+    const int ox = (int)(p.texloc % kAtlasDim), oy = (int)(p.texloc / kAtlasDim);
+    const bool shrink = p.w > m->patch_w || p.h > m->patch_h;
+    const int ew = shrink ? m->patch_w : p.w, eh = shrink ? m->patch_h : p.h;
+    if (ox + ew > kAtlasDim || oy + eh > kAtlasDim) return fail(m, TF_ERR_INVALID, "tf_atlas_update: slot outside the atlas");
+    pd[i] = PatchDev{p.texloc, m->slots[s].rgb, p.x, p.y, p.w, p.h};
+  }
+  if (n > m->patch_cap) {
+    cudaFree(m->patch_d);
+    m->patch_cap = (int)std::max<int64_t>(n, 4096);
+    CUDA_OK(m, dmalloc(&m->patch_d, (size_t)m->patch_cap));
+  }
+  // pageable source: the copy is staged before the call returns, so `pd` may go out of scope
+  CUDA_OK(m, cudaMemcpyAsync(m->patch_d, pd.data(), (size_t)n * sizeof(PatchDev), cudaMemcpyHostToDevice, m->stream));
+  atlas_update_kernel<<<(unsigned)n, kThreads, 0, m->stream>>>(m->patch_d, m->atlas, m->W, m->patch_w, m->patch_h);
+  if (int rc = check_kernel(m, "atlas_update_kernel")) return rc;
+  m->counters.h2d_bytes += n * (int64_t)sizeof(PatchDev);
+  return TF_OK;
+}
+
+int tf_atlas_download(tf_map* m, uint64_t hot_start, uint64_t hot_end, uint8_t* rgb_out) {
+  if (!m || !rgb_out || hot_end < hot_start || hot_end > (uint64_t)kAtlasDim * kAtlasDim)
+    return fail(m, TF_ERR_INVALID, "tf_atlas_download: bad range");
+  if (int rc = ensure_atlas(m)) return rc;
+  const size_t nb = (size_t)(hot_end - hot_start) * 3;
+  CUDA_OK(m, cudaMemcpyAsync(rgb_out, m->atlas + hot_start * 3, nb, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  m->counters.d2h_bytes += nb;
+  return TF_OK;
+}
+
+// ---- counters / profiling ------------------------------------------------------------------------
+
+int tf_get_counters(tf_map* m, tf_counters* out) {
+  if (!m || !out) return TF_ERR_INVALID;
+  m->counters.pool_used = m->n_live;
+  *out = m->counters;
+  return TF_OK;
+}
+
+int tf_set_profiling(tf_map* m, int enable) {
+  if (!m) return TF_ERR_INVALID;
+  m->prof = enable != 0;
+  return TF_OK;
+}
+
+int tf_get_kernel_time(tf_map* m, int reset, double* integrate_ms, int64_t* launches, double* bytes) {
+  if (!m) return TF_ERR_INVALID;
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  prof_collect(m, 0);
+  if (integrate_ms) *integrate_ms = m->prof_ms;
+  if (launches) *launches = m->prof_launches;
+  if (bytes) *bytes = m->prof_bytes;
+  if (reset) {
+    m->prof_ms = 0;
+    m->prof_bytes = 0;
+    m->prof_launches = 0;
+  }
+  return TF_OK;
+}
+
+}  // extern "C"
