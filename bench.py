@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — fused RGB-D frames/s of the fusion hot path (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json configs[1] — the seeded synthetic 640x480 room
+sequence (300 poses, every 10th frame a key-frame with colour + quality, the others
+depth-only) fused at 0.005 m voxels.  One "step" = one frame through
+Prepare + Integrate + Finalize (MobileFusion::IntegrateFrame, GCFusion/MobileFusion.cpp:223-250).
+
+  value     frames/s with the frames already resident in HBM (device-event timed)
+  e2e       frames/s through the public C ABI with HOST (pinned) buffers: H2D of the frame's
+            planes and D2H of the chunk list / flags / quality sums inside the timed region
+  roofline  integrate_kernel: algorithmic bytes / CUDA-event kernel time vs measured HBM peak
+  cpu_baseline  the CPU oracle (AVX2 restatement of the reference) on a bounded sample
+
+`--impl reference` times the reference's CPU algorithm (oracle port; the reference itself
+cannot be built here) with the reference's thread policy on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEQ_FRAMES = 300
+KEYFRAME_EVERY = 10
+METRIC = "fused RGB-D frames/s (640x480, 5 mm voxels)"
+
+
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks and throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.gpu, self.samples, self.stop_flag, self.th = gpu, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_data(n_frames, device):
+    from texturefusion_b200 import synth
+    cam = synth.Camera()
+    t0 = time.time()
+    seq = synth.make_sequence(n_frames, cam=cam, total=SEQ_FRAMES, keyframe_every=KEYFRAME_EVERY, device=device)
+    return seq, time.time() - t0
+
+
+def run_cpu_reference(seq, res, steps, warmup, budget_s, threads):
+    """The reference's CPU path (oracle port): Prepare + Integrate + Finalize per frame."""
+    from oracle import OracleMap
+    o = OracleMap(res, threads=threads)
+    frames = seq.frames
+    rgba = {fr.index: fr.rgba() for fr in frames if fr.is_keyframe}
+    k = 0
+    for _ in range(warmup):
+        fr = frames[k % len(frames)]
+        o.integrate_frame(fr.depth, rgba.get(fr.index), fr.quality, fr.pose, seq.cam, fr.index if fr.is_keyframe else -1)
+        k += 1
+    t_total, done, vox = 0.0, 0, 0
+    for _ in range(steps):
+        fr = frames[k % len(frames)]
+        t0 = time.perf_counter()
+        n, _ = o.integrate_frame(fr.depth, rgba.get(fr.index), fr.quality, fr.pose, seq.cam,
+                                 fr.index if fr.is_keyframe else -1)
+        t_total += time.perf_counter() - t0
+        vox += n * 512
+        done += 1
+        k += 1
+        if t_total > budget_s:
+            break
+    return {"fps": done / t_total, "frames": done, "seconds": t_total, "voxel_updates_per_s": vox / t_total,
+            "cores": o.threads_used}
+
+
+def flush_l2(torch, buf):
+    buf.fill_(1.0)  # 512 MiB write > 126 MB L2
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=SEQ_FRAMES)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--res", type=float, default=0.005)
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import torch
+    have_cuda = torch.cuda.is_available()
+    n_need = min(SEQ_FRAMES, args.steps + args.warmup)
+    config = {"workload": "configs[1]: synthetic 640x480 room sequence (300 poses, key-frame every 10th frame with "
+                          "colour+quality, others depth-only), TSDF + voxel colour fusion, Prepare+Integrate+Finalize per frame",
+              "voxel_res_m": args.res, "frames_in_sequence": SEQ_FRAMES, "image": "640x480",
+              "l2": "flushed between timed steps (512 MiB write), flush excluded from the timed region",
+              "parallelism": f"chunk-sharded x{args.gpus}" if args.gpus > 1 else "single GPU"}
+
+    # ---------------- reference arm: CPU implementation on the host cores -----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        seq, _ = make_data(n_need, "cuda" if have_cuda else "cpu")
+        steps = min(args.steps, 120)  # bounded sample: ~10-30 s of CPU work
+        r = run_cpu_reference(seq, args.res, steps, min(args.warmup, 3), 60.0, threads=0)
+        line = {"impl": "reference", "metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus,
+                "steps": r["frames"], "warmup": min(args.warmup, 3), "ms_per_step": 1e3 / r["fps"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
+                                 "sample": f"first {r['frames']} frames of the workload after {min(args.warmup, 3)} warm-up frames, "
+                                           "oracle port with the reference's parallel_for policy"},
+                "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "voxel_updates_per_s": r["voxel_updates_per_s"]}
+        print(json.dumps(line))
+        return
+
+    # ---------------- our arm ------------------------------------------------------------------
+    if not have_cuda:
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    from texturefusion_b200 import capi
+    import ctypes as C
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = f"cuda:{local_rank}"
+    seq, gen_s = make_data(n_need, dev)
+    cam = seq.cam
+    frames = seq.frames
+    nf = len(frames)
+    peak_gbs, peak_src = load_peak()
+
+    def new_map():
+        return capi.Map(args.res, device=local_rank, n_ranks=world, rank=rank, max_frames=nf + 8,
+                        max_chunks=1 << 19)
+
+    flush_buf = torch.empty(128 * 1024 * 1024, dtype=torch.float32, device=dev)
+    rgba = {fr.index: fr.rgba() for fr in frames if fr.is_keyframe}
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ===== pass 1: frames resident in HBM, device-event timing =====================================
+    m = new_map()
+    for fr in frames:
+        m.upload_frame(fr.index, fr.depth, rgba.get(fr.index), fr.quality if fr.is_keyframe else None)
+    m.sync()
+    ext = torch.cuda.ExternalStream(m.stream(), device=dev)
+    ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k = 0
+    for _ in range(args.warmup):
+        fr = frames[k % nf]
+        m.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam, want_lists=False)
+        k += 1
+    c0 = m.counters()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    vox = 0
+    chunks = 0
+    for s in range(args.steps):
+        fr = frames[k % nf]
+        flush_l2(torch, flush_buf)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(ext):
+            ev_a[s].record()
+        st, *_ = m.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam, want_lists=False)
+        with torch.cuda.stream(ext):
+            ev_b[s].record()
+        vox += st.voxel_updates
+        chunks += st.n_chunks
+        k += 1
+    barrier()
+    clocks = sampler.stop()
+    c1 = m.counters()
+    dev_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b))
+    dev_ms = max_over_ranks(dev_ms)
+    launches = c1["kernel_launches"] - c0["kernel_launches"]
+    value = args.steps / (dev_ms * 1e-3)
+    live_chunks = m.chunk_count()
+    m.close()
+
+    # ===== pass 2: kernel-level timing of integrate_kernel (roofline) ================================
+    m = new_map()
+    for fr in frames:
+        m.upload_frame(fr.index, fr.depth, rgba.get(fr.index), fr.quality if fr.is_keyframe else None)
+    m.sync()
+    k = 0
+    for _ in range(args.warmup):
+        fr = frames[k % nf]
+        m.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam, want_lists=False)
+        k += 1
+    m.set_profiling(True)
+    m.kernel_time(reset=True)
+    for s in range(args.steps):
+        fr = frames[k % nf]
+        flush_l2(torch, flush_buf)
+        torch.cuda.synchronize()
+        m.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam, want_lists=False)
+        k += 1
+    k_ms, k_n, k_bytes = m.kernel_time(reset=True)
+    m.close()
+    achieved = (k_bytes / 1e9) / (k_ms * 1e-3) if k_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "launches": k_n, "avg_launch_us": 1e3 * k_ms / max(k_n, 1),
+                "algorithmic_bytes_per_launch": k_bytes / max(k_n, 1),
+                "kernel_share_of_step": k_ms / dev_ms if dev_ms > 0 else None}
+
+    # ===== pass 3: end to end through the C ABI with host buffers ======================================
+    m = new_map()
+    pin_d = [capi.PinnedBuffer((cam.height, cam.width), np.float32) for _ in range(nf)]
+    pin_c, pin_q = {}, {}
+    for i, fr in enumerate(frames):
+        pin_d[i].array[...] = fr.depth
+        if fr.is_keyframe:
+            pin_c[i] = capi.PinnedBuffer((cam.height, cam.width, 4), np.uint8)
+            pin_c[i].array[...] = rgba[fr.index]
+            pin_q[i] = capi.PinnedBuffer((cam.height, cam.width), np.float32)
+            pin_q[i].array[...] = fr.quality
+    cap = 1 << 16
+    out_ids = np.empty((cap, 3), np.int32)
+    out_new = np.empty(cap, np.uint8)
+    out_upd = np.empty(cap, np.uint8)
+    out_q = np.empty(cap, np.float32)
+    L = m.L
+    camc = capi.make_camera(cam)
+    poses = [capi.make_pose(fr.pose) for fr in frames]
+    st = capi.FrameStats()
+    vp = C.c_void_p
+
+    def e2e_step(i):
+        fr = frames[i]
+        if dist is not None:
+            # rank 0 ingests the frame; its planes are broadcast over NVLink into every rank's store
+            d_ptr, c_ptr, q_ptr = m.frame_device_ptrs(fr.index, fr.is_keyframe)
+            if rank == 0:
+                rc = L.tf_upload_frame(m.h, fr.index, vp(pin_d[i].ptr), vp(pin_c[i].ptr) if fr.is_keyframe else None,
+                                       vp(pin_q[i].ptr) if fr.is_keyframe else None)
+                assert rc == 0
+                m.sync()
+            planes = [(d_ptr, 4)] + ([(c_ptr, 4), (q_ptr, 4)] if fr.is_keyframe else [])
+            for ptr, _ in planes:
+                t = dev_tensor(torch, ptr, cam.height * cam.width, local_rank)
+                dist.broadcast(t, src=0)
+            torch.cuda.synchronize()
+        else:
+            rc = L.tf_upload_frame(m.h, fr.index, vp(pin_d[i].ptr), vp(pin_c[i].ptr) if fr.is_keyframe else None,
+                                   vp(pin_q[i].ptr) if fr.is_keyframe else None)
+            assert rc == 0
+        rc = L.tf_integrate_frame(m.h, fr.index, int(fr.is_keyframe), C.byref(poses[i]), C.byref(camc), C.byref(st),
+                                  out_ids.ctypes.data_as(vp), out_new.ctypes.data_as(vp), out_upd.ctypes.data_as(vp),
+                                  out_q.ctypes.data_as(vp), cap)
+        assert rc == 0, L.tf_last_error(m.h)
+        return st.n_chunks
+
+    k = 0
+    for _ in range(args.warmup):
+        e2e_step(k % nf)
+        k += 1
+    c0 = m.counters()
+    barrier()
+    e2e_s = 0.0
+    for s in range(args.steps):
+        flush_l2(torch, flush_buf)
+        barrier() if dist is not None else torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_step(k % nf)
+        e2e_s += time.perf_counter() - t0
+        k += 1
+    barrier()
+    c1 = m.counters()
+    e2e_s = max_over_ranks(e2e_s)
+    e2e = {"value": args.steps / e2e_s, "unit": "frames/s",
+           "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / args.steps,
+           "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / args.steps,
+           "ms_per_step": 1e3 * e2e_s / args.steps}
+    m.close()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ===== CPU baseline (rank 0, N=1 only): oracle port on a bounded sample ================================
+    cpu_baseline = None
+    if args.gpus == 1 and not args.no_cpu_baseline:
+        r = run_cpu_reference(seq, args.res, min(args.steps, nf), 2, args.cpu_budget, threads=0)
+        cpu_baseline = {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
+                        "sample": f"first {r['frames']} frames of the same workload ({r['seconds']:.1f} s of CPU work), "
+                                  "oracle port, reference parallel_for policy (hardware_concurrency-2 threads, >=1000 chunks per group)",
+                        "voxel_updates_per_s": r["voxel_updates_per_s"]}
+
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "voxel_updates_per_s": vox / (dev_ms * 1e-3), "chunks_per_frame": chunks / args.steps,
+            "live_chunks": live_chunks, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks, "data_gen_s": gen_s}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+class _DevPtr:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def dev_tensor(torch, ptr, n_words, device):
+    """A torch view over a raw device plane of the frame store (for the NCCL broadcast)."""
+    return torch.as_tensor(_DevPtr(ptr, n_words), device=f"cuda:{device}")
+
+
+if __name__ == "__main__":
+    main()
