@@ -40,3 +40,40 @@ def assert_maps_equal(gpu_map, oracle_map, trunc_tol=True, what=""):
     tol = 1e-5 * 0.009
     assert np.all(np.abs(gs - os_) <= tol), f"{what}: sdf differs by {np.abs(gs - os_).max()}"
     return bool(np.array_equal(gs.view(np.uint32), os_.view(np.uint32)))
+
+
+class GpuAsOracle:
+    """Adapter: drives the CUDA library through the C ABI with the oracle's call shapes
+    (images by value), so protocol drivers can run either implementation."""
+
+    SCRATCH = 0x7F000000
+
+    def __init__(self, res, **kw):
+        from texturefusion_b200 import capi
+        self.m = capi.Map(res, **kw)
+        self.mesh = {}
+
+    def prepare(self, depth, pose, cam):
+        self.m.upload_frame(self.SCRATCH, depth)
+        return self.m.prepare(self.SCRATCH, pose, cam)
+
+    def integrate(self, depth, rgba, quality, pose, cam, ids, flag, keyframe_id=-1, needs_update=None):
+        self.m.upload_frame(self.SCRATCH, depth, rgba, quality if rgba is not None else None)
+        return self.m.integrate(self.SCRATCH, rgba is not None, pose, cam, ids, flag, needs_update)
+
+    def finalize(self, ids, needs_update, is_new):
+        ids = np.asarray(ids, np.int32).reshape(-1, 3)
+        nu = np.asarray(needs_update) != 0
+        garbage = ids[(~nu) & (np.asarray(is_new) != 0)]
+        if len(garbage):
+            self.m.remove_chunks(garbage)
+        return ids[nu].copy()
+
+    def list_chunks(self):
+        return self.m.list_chunks()
+
+    def download_chunks(self, ids):
+        return self.m.download_chunks(ids)
+
+    def chunk_count(self):
+        return self.m.chunk_count()
