@@ -258,8 +258,9 @@ def main():
         fr = frames[k % nf]
         m.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam, want_lists=False)
         k += 1
-    m.set_profiling(True)
+    m.set_profiling(2)
     m.kernel_time(reset=True)
+    m.stage_times(reset=True)
     for s in range(args.steps):
         fr = frames[k % nf]
         flush_l2(torch, flush_buf)
@@ -267,6 +268,7 @@ def main():
         m.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam, want_lists=False)
         k += 1
     k_ms, k_n, k_bytes = m.kernel_time(reset=True)
+    stage_us = {k: 1e3 * v / args.steps for k, v in m.stage_times().items()}
     m.close()
     achieved = (k_bytes / 1e9) / (k_ms * 1e-3) if k_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
@@ -364,7 +366,8 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "voxel_updates_per_s": vox / (dev_ms * 1e-3), "chunks_per_frame": chunks / args.steps,
             "live_chunks": live_chunks, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "data_gen_s": gen_s}
+            "gpu_launches": int(launches), "clocks": clocks, "data_gen_s": gen_s,
+            "stage_us_per_frame": stage_us}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

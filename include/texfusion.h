@@ -228,9 +228,17 @@ int tf_get_counters(tf_map* m, tf_counters* out);
 void* tf_stream(tf_map* m);
 /* device time (ms) spent in the integrate kernel since the last call with reset != 0;
  * measured with CUDA events on the map's stream when enabled via tf_set_profiling. */
-int tf_set_profiling(tf_map* m, int enable);
+int tf_set_profiling(tf_map* m, int level /* 0 off, 1 integrate kernel, 2 every pipeline stage */);
+/* device time (ms) per stage of the fused pipeline since the last reset, level 2 only:
+ * [bbox, cull_coarse, cull_fine, alloc, integrate, finalize] */
+int tf_get_stage_times(tf_map* m, int reset, double* ms6);
 int tf_get_kernel_time(tf_map* m, int reset, double* integrate_ms, int64_t* integrate_launches,
                        double* integrate_bytes);
+
+/* Test hook: runs both pixel-projection paths of integrate_kernel (tf_device.cuh:
+ * project_fast / project_exact) on n caller-provided (c, cz) pairs. */
+int tf_debug_project(tf_map* m, const float* c, const float* cz, int64_t n, float f, float ch,
+                     int32_t* u_fast, int32_t* u_exact, uint8_t* accepted);
 
 #ifdef __cplusplus
 }

@@ -193,3 +193,31 @@ def test_errors_and_edge_cases():
     assert g.chunk_count() == total - 5
     g.reset()
     assert g.chunk_count() == 0
+
+
+def test_fast_projection_never_disagrees_with_exact_path():
+    """integrate_kernel rounds pixel coordinates with a division-free fast path that must either
+    agree with the reference's three-op expression or decline (tf_device.cuh: project_fast).
+    Random operands over the working range plus operands engineered to land next to the
+    rounding boundaries k + 0.5, zeros, negatives, tiny/huge depths, NaN and inf."""
+    g = capi.Map(0.02)
+    rng = np.random.RandomState(5)
+    n = 1 << 22
+    f, ch = np.float32(525.0), np.float32(319.5)
+    cz = rng.uniform(0.05, 6.0, n).astype(np.float32)
+    c = (rng.uniform(-1.2, 1.2, n) * cz).astype(np.float32)
+    # engineered: choose c so that (c/cz)*f + ch is within a few ulps of k + 0.5
+    k = rng.randint(-50, 700, n // 2)
+    target = (k + 0.5 + rng.uniform(-2e-3, 2e-3, n // 2)).astype(np.float64)
+    c[: n // 2] = ((target - float(ch)) / float(f) * cz[: n // 2].astype(np.float64)).astype(np.float32)
+    special = np.array([0.0, -0.0, 1e-30, -1e-30, 1e-40, 1e30, -1e30, np.inf, -np.inf, np.nan, 3e38, 1.0], np.float32)
+    cs, zs = np.meshgrid(special, special)
+    c = np.concatenate([c, cs.ravel()])
+    cz = np.concatenate([cz, zs.ravel()])
+    tot_acc = 0
+    for (ff, cc) in ((f, ch), (np.float32(525.0), np.float32(239.5)), (np.float32(131.0), np.float32(79.5))):
+        uf, ue, acc = g.debug_project(c, cz, ff, cc)
+        bad = (acc != 0) & (uf != ue)
+        assert not bad.any(), f"{bad.sum()} accepted fast-path results differ, e.g. c={c[bad][:3]} cz={cz[bad][:3]}"
+        tot_acc += acc[: n].mean()
+    assert tot_acc / 3 > 0.5  # the fast path is actually taken (engineered half declines by design)

@@ -23,7 +23,7 @@ EXPORTS = [
     "tf_prepare", "tf_integrate", "tf_integrate_group", "tf_remove_chunks", "tf_integrate_frame",
     "tf_integrate_batch", "tf_has_chunk", "tf_chunk_count", "tf_list_chunks", "tf_download_chunks",
     "tf_atlas_alloc_slot", "tf_atlas_update", "tf_atlas_download", "tf_atlas_patch_size", "tf_sync",
-    "tf_get_counters", "tf_stream", "tf_set_profiling", "tf_get_kernel_time",
+    "tf_get_counters", "tf_stream", "tf_set_profiling", "tf_get_kernel_time", "tf_get_stage_times", "tf_debug_project",
 ]
 
 
@@ -129,6 +129,8 @@ def load() -> C.CDLL:
     L.tf_stream.restype = vp
     L.tf_set_profiling.argtypes = [vp, C.c_int]
     L.tf_get_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]
+    L.tf_get_stage_times.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    L.tf_debug_project.argtypes = [vp, vp, vp, i64, C.c_float, C.c_float, vp, vp, vp]
     _LIB = L
     return L
 
@@ -389,8 +391,21 @@ class Map:
     def stream(self) -> int:
         return int(self.L.tf_stream(self.h) or 0)
 
-    def set_profiling(self, enable: bool):
-        self._check(self.L.tf_set_profiling(self.h, int(enable)))
+    def set_profiling(self, level):
+        self._check(self.L.tf_set_profiling(self.h, int(level)))
+
+    def debug_project(self, c, cz, f, ch):
+        c = np.ascontiguousarray(c, np.float32)
+        cz = np.ascontiguousarray(cz, np.float32)
+        n = c.size
+        uf, ue, acc = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.uint8)
+        self._check(self.L.tf_debug_project(self.h, _p(c), _p(cz), n, C.c_float(f), C.c_float(ch), _p(uf), _p(ue), _p(acc)))
+        return uf, ue, acc
+
+    def stage_times(self, reset=True) -> dict:
+        arr = (C.c_double * 6)()
+        self._check(self.L.tf_get_stage_times(self.h, int(reset), arr))
+        return dict(zip(("bbox", "cull_coarse", "cull_fine", "alloc", "integrate", "finalize"), arr))
 
     def kernel_time(self, reset=True):
         ms, n, b = C.c_double(), C.c_int64(), C.c_double()

@@ -38,7 +38,9 @@ struct FrameSlot {
 struct EventPair {
   cudaEvent_t a, b;
   double bytes;
+  int stage;  // 0 bbox, 1 coarse, 2 fine, 3 alloc, 4 integrate, 5 finalize
 };
+constexpr int kStages = 6;
 
 }  // namespace
 
@@ -47,7 +49,7 @@ struct tf_map {
   int W = 0, H = 0, npix = 0;
   cudaStream_t stream = nullptr;
   std::string err;
-  int sm_count = 0, grid = 0, grid_integrate = 0;
+  int sm_count = 0, grid = 0, grid_integrate = 0, grid_integrate_c = 0;
 
   MapDev md{};
   FrameState* fs = nullptr;
@@ -106,10 +108,11 @@ struct tf_map {
   tf_counters counters{};
 
   // profiling of the integrate kernel
-  bool prof = false;
+  int prof = 0;  // 1: integrate kernel only, 2: every stage of the fused pipeline
   std::vector<EventPair> ev_pool, ev_pending;
   double prof_ms = 0, prof_bytes = 0;
   int64_t prof_launches = 0;
+  double stage_ms[kStages] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -204,9 +207,10 @@ void prof_begin(tf_map* m, EventPair& ep) {
   }
   cudaEventRecord(ep.a, m->stream);
 }
-void prof_end(tf_map* m, EventPair& ep) {
+void prof_end(tf_map* m, EventPair& ep, int stage = 4) {
   cudaEventRecord(ep.b, m->stream);
   ep.bytes = -1;
+  ep.stage = stage;
   m->ev_pending.push_back(ep);
 }
 // after a stream sync: fold finished event pairs; `bytes` = algorithmic bytes of the launch
@@ -215,9 +219,12 @@ void prof_collect(tf_map* m, double bytes_last) {
     EventPair& ep = m->ev_pending[i];
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) {
-      m->prof_ms += ms;
-      m->prof_launches++;
-      m->prof_bytes += (ep.bytes >= 0 ? ep.bytes : bytes_last);
+      m->stage_ms[ep.stage] += ms;
+      if (ep.stage == 4) {
+        m->prof_ms += ms;
+        m->prof_launches++;
+        m->prof_bytes += (ep.bytes >= 0 ? ep.bytes : bytes_last);
+      }
     }
     m->ev_pool.push_back(ep);
   }
@@ -236,17 +243,25 @@ double algorithmic_bytes(const tf_map* m, int64_t n_chunks, const bool* color, i
 // ---- pipeline stages -------------------------------------------------------------------------
 
 int launch_cull(tf_map* m, const CullParams& cp, const float* depth, int do_alloc) {
+  EventPair ep;
+  const bool st = m->prof >= 2;
+  if (st) prof_begin(m, ep);
   bbox_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->partial, m->cand_cap);
+  if (st) { prof_end(m, ep, 0); prof_begin(m, ep); }
   if (int rc = check_kernel(m, "bbox_kernel")) return rc;
   cull_coarse_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->words_c, m->coarse_list,
                                                           m->fine_words_cap);
+  if (st) { prof_end(m, ep, 1); prof_begin(m, ep); }
   if (int rc = check_kernel(m, "cull_coarse_kernel")) return rc;
   cull_fine_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->coarse_list, m->words_f, m->word_off,
                                                         m->cfg.n_ranks, m->cfg.rank, m->list_cap);
+  if (st) prof_end(m, ep, 2);
   if (int rc = check_kernel(m, "cull_fine_kernel")) return rc;
   if (do_alloc >= 0) {
+    if (st) prof_begin(m, ep);
     alloc_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, m->md, m->fs, m->coarse_list, m->words_f, m->word_off,
                                                       m->list_ids, m->list_slots, m->list_new, do_alloc);
+    if (st) prof_end(m, ep, 3);
     if (int rc = check_kernel(m, "alloc_kernel")) return rc;
   }
   return TF_OK;
@@ -255,8 +270,14 @@ int launch_cull(tf_map* m, const CullParams& cp, const float* depth, int do_allo
 int launch_integrate(tf_map* m, const GroupParams& gp, const int* n_dev, int n_host, double bytes) {
   EventPair ep;
   if (m->prof) prof_begin(m, ep);
-  integrate_kernel<<<m->grid_integrate, kThreads, 0, m->stream>>>(gp, m->md, m->list_slots, n_dev, n_host,
-                                                                  m->list_upd, m->list_q);
+  bool any_color = false;
+  for (int f = 0; f < gp.n_frames; f++) any_color |= gp.f[f].rgba != nullptr;
+  if (any_color)
+    integrate_kernel<true><<<m->grid_integrate_c, kThreads, integrate_smem_bytes(gp.n_frames), m->stream>>>(
+        gp, m->md, m->list_slots, m->list_ids, n_dev, n_host, m->list_upd, m->list_q);
+  else
+    integrate_kernel<false><<<m->grid_integrate, kThreads, integrate_smem_bytes(gp.n_frames), m->stream>>>(
+        gp, m->md, m->list_slots, m->list_ids, n_dev, n_host, m->list_upd, m->list_q);
   if (m->prof) {
     prof_end(m, ep);
     m->ev_pending.back().bytes = bytes;
@@ -380,6 +401,11 @@ int tf_create(tf_map** out, const tf_config* cfg) {
     delete m;
     return TF_ERR_INVALID;
   }
+  if (m->W > 2048 || m->H > 2048) {  // bound used by project_fast's error analysis (tf_device.cuh)
+    g_create_error = "frame larger than 2048x2048";
+    delete m;
+    return TF_ERR_INVALID;
+  }
   auto bail = [&](int rc) {
     g_create_error = m->err;
     tf_destroy(m);
@@ -399,7 +425,14 @@ int tf_create(tf_map** out, const tf_config* cfg) {
   m->sm_count = prop.multiProcessorCount;
   C_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   int occ = 1;
-  C_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, integrate_kernel, kThreads, 0));
+  C_OK(cudaFuncSetAttribute(integrate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)integrate_smem_bytes(kMaxGroupFrames)));
+  C_OK(cudaFuncSetAttribute(integrate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)integrate_smem_bytes(kMaxGroupFrames)));
+  int occ_c = 1;
+  C_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, integrate_kernel<false>, kThreads, integrate_smem_bytes(1)));
+  C_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, integrate_kernel<true>, kThreads, integrate_smem_bytes(1)));
+  m->grid_integrate_c = m->sm_count * std::max(1, occ_c);
   m->grid = m->sm_count * 2;
   m->grid_integrate = m->sm_count * std::max(1, occ);
 
@@ -645,10 +678,13 @@ static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, co
   if (int rc = launch_cull(m, cp, m->slots[s].depth, 1)) return rc;
   if (int rc = launch_integrate(m, gp, &m->fs->n_list, 0, -1)) return rc;
   const int ocap = (int)std::min<int64_t>(cap, m->list_cap);
+  EventPair epf;
+  if (m->prof >= 2) prof_begin(m, epf);
   finalize_kernel<<<m->grid, kThreads, 0, m->stream>>>(
       m->md, m->fs, m->list_ids, m->list_slots, m->list_new, m->list_upd, m->list_q, 1,
       ids_out ? m->out_ids_d : nullptr, new_out ? m->out_new_d : nullptr, upd_out ? m->out_upd_d : nullptr,
       q_out ? m->out_q_d : nullptr, ocap, m->res_d);
+  if (m->prof >= 2) prof_end(m, epf, 5);
   if (int rc = check_kernel(m, "finalize_kernel")) return rc;
   CUDA_OK(m, cudaStreamSynchronize(m->stream));
   absorb_result(m);
@@ -732,7 +768,7 @@ int tf_has_chunk(tf_map* m, tf_chunk_id id) {
   if (int rc = lookup_ids(m, &id, 1, false)) return rc;
   int slot = -1;
   CUDA_OK(m, cudaMemcpy(&slot, m->list_slots, sizeof(int), cudaMemcpyDeviceToHost));
-  return slot >= 0 ? 1 : 0;
+  return slot >= 0 ? 1 : 0;  // (a lazy bit may be set; the sign is what matters)
 }
 
 int64_t tf_chunk_count(tf_map* m) { return m ? m->n_live : TF_ERR_INVALID; }
@@ -875,7 +911,45 @@ int tf_get_counters(tf_map* m, tf_counters* out) {
 
 int tf_set_profiling(tf_map* m, int enable) {
   if (!m) return TF_ERR_INVALID;
-  m->prof = enable != 0;
+  m->prof = enable;
+  return TF_OK;
+}
+
+int tf_debug_project(tf_map* m, const float* c, const float* cz, int64_t n, float f, float ch, int32_t* u_fast,
+                     int32_t* u_exact, uint8_t* accepted) {
+  if (!m || !c || !cz || !u_fast || !u_exact || !accepted || n <= 0 || n > (1 << 26))
+    return fail(m, TF_ERR_INVALID, "tf_debug_project: bad argument");
+  float *dc = nullptr, *dz = nullptr;
+  int *duf = nullptr, *due = nullptr;
+  unsigned char* da = nullptr;
+  int rc = TF_OK;
+  auto ok = [&](cudaError_t e) {
+    if (e != cudaSuccess && rc == TF_OK) rc = fail(m, TF_ERR_CUDA, cudaGetErrorString(e));
+    return e == cudaSuccess;
+  };
+  if (ok(dmalloc(&dc, (size_t)n)) && ok(dmalloc(&dz, (size_t)n)) && ok(dmalloc(&duf, (size_t)n)) &&
+      ok(dmalloc(&due, (size_t)n)) && ok(dmalloc(&da, (size_t)n)) &&
+      ok(cudaMemcpyAsync(dc, c, n * 4, cudaMemcpyHostToDevice, m->stream)) &&
+      ok(cudaMemcpyAsync(dz, cz, n * 4, cudaMemcpyHostToDevice, m->stream))) {
+    debug_project_kernel<<<m->grid, kThreads, 0, m->stream>>>(dc, dz, (int)n, f, ch, duf, due, da);
+    ok(cudaGetLastError());
+    ok(cudaMemcpyAsync(u_fast, duf, n * 4, cudaMemcpyDeviceToHost, m->stream));
+    ok(cudaMemcpyAsync(u_exact, due, n * 4, cudaMemcpyDeviceToHost, m->stream));
+    ok(cudaMemcpyAsync(accepted, da, n, cudaMemcpyDeviceToHost, m->stream));
+    ok(cudaStreamSynchronize(m->stream));
+  }
+  cudaFree(dc); cudaFree(dz); cudaFree(duf); cudaFree(due); cudaFree(da);
+  return rc;
+}
+
+int tf_get_stage_times(tf_map* m, int reset, double* ms6) {
+  if (!m || !ms6) return TF_ERR_INVALID;
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  prof_collect(m, 0);
+  for (int i = 0; i < kStages; i++) {
+    ms6[i] = m->stage_ms[i];
+    if (reset) m->stage_ms[i] = 0;
+  }
   return TF_OK;
 }
 
