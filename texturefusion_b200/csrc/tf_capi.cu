@@ -67,6 +67,8 @@ struct tf_map {
   unsigned char* list_new = nullptr;
   unsigned* list_upd = nullptr;
   float* list_q = nullptr;
+  float* list_setup = nullptr;  // [list_cap][setup_frames][8]: per-(chunk, frame) constants
+  int setup_frames = 0;
 
   // mapped pinned result + output staging
   FrameResultHost* res_h = nullptr;
@@ -242,7 +244,20 @@ double algorithmic_bytes(const tf_map* m, int64_t n_chunks, const bool* color, i
 
 // ---- pipeline stages -------------------------------------------------------------------------
 
-int launch_cull(tf_map* m, const CullParams& cp, const float* depth, int do_alloc) {
+int ensure_setup(tf_map* m, int n_frames) {
+  if (n_frames <= m->setup_frames) return TF_OK;
+  cudaStreamSynchronize(m->stream);
+  cudaFree(m->list_setup);
+  m->list_setup = nullptr;
+  m->setup_frames = 0;
+  CUDA_OK(m, dmalloc(&m->list_setup, (size_t)m->list_cap * n_frames * kSetupStride));
+  m->setup_frames = n_frames;
+  return TF_OK;
+}
+
+// gp: the frames that will be integrated over the list (n_frames == 0: prepare only)
+int launch_cull(tf_map* m, const CullParams& cp, const GroupParams& gp, const float* depth, int do_alloc) {
+  if (int rc = ensure_setup(m, std::max(1, gp.n_frames))) return rc;
   EventPair ep;
   const bool st = m->prof >= 2;
   if (st) prof_begin(m, ep);
@@ -259,8 +274,8 @@ int launch_cull(tf_map* m, const CullParams& cp, const float* depth, int do_allo
   if (int rc = check_kernel(m, "cull_fine_kernel")) return rc;
   if (do_alloc >= 0) {
     if (st) prof_begin(m, ep);
-    alloc_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, m->md, m->fs, m->coarse_list, m->words_f, m->word_off,
-                                                      m->list_ids, m->list_slots, m->list_new, do_alloc);
+    alloc_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, gp, m->md, m->fs, m->coarse_list, m->words_f, m->word_off,
+                                                      m->list_ids, m->list_slots, m->list_new, m->list_setup, do_alloc);
     if (st) prof_end(m, ep, 3);
     if (int rc = check_kernel(m, "alloc_kernel")) return rc;
   }
@@ -274,10 +289,10 @@ int launch_integrate(tf_map* m, const GroupParams& gp, const int* n_dev, int n_h
   for (int f = 0; f < gp.n_frames; f++) any_color |= gp.f[f].rgba != nullptr;
   if (any_color)
     integrate_kernel<true><<<m->grid_integrate_c, kThreads, integrate_smem_bytes(gp.n_frames), m->stream>>>(
-        gp, m->md, m->list_slots, m->list_ids, n_dev, n_host, m->list_upd, m->list_q);
+        gp, m->md, m->list_slots, m->list_setup, n_dev, n_host, m->list_upd, m->list_q);
   else
     integrate_kernel<false><<<m->grid_integrate, kThreads, integrate_smem_bytes(gp.n_frames), m->stream>>>(
-        gp, m->md, m->list_slots, m->list_ids, n_dev, n_host, m->list_upd, m->list_q);
+        gp, m->md, m->list_slots, m->list_setup, n_dev, n_host, m->list_upd, m->list_q);
   if (m->prof) {
     prof_end(m, ep);
     m->ev_pending.back().bytes = bytes;
@@ -312,10 +327,13 @@ int upload_ids(tf_map* m, const tf_chunk_id* ids, int64_t n) {
 }
 
 // ids (host) -> list_slots (device); fails with TF_ERR_NOT_FOUND before anything is modified.
-int lookup_ids(tf_map* m, const tf_chunk_id* ids, int64_t n, bool must_exist) {
+int lookup_ids(tf_map* m, const tf_chunk_id* ids, int64_t n, bool must_exist, const GroupParams* gp = nullptr) {
+  static const GroupParams kNoFrames{};  // n_frames == 0
+  if (int rc = ensure_setup(m, gp ? gp->n_frames : 1)) return rc;
   if (int rc = upload_ids(m, ids, n)) return rc;
   const int grid = (int)std::min<int64_t>(m->grid, (n + kThreads - 1) / kThreads);
-  lookup_kernel<<<std::max(grid, 1), kThreads, 0, m->stream>>>(m->md, m->fs, m->list_ids, (int)n, m->list_slots);
+  lookup_kernel<<<std::max(grid, 1), kThreads, 0, m->stream>>>(gp ? *gp : kNoFrames, m->md, m->fs, m->list_ids, (int)n,
+                                                               m->list_slots, m->list_setup);
   if (int rc = check_kernel(m, "lookup_kernel")) return rc;
   publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);
   if (int rc = check_kernel(m, "publish_kernel")) return rc;
@@ -352,7 +370,7 @@ void tf_destroy(tf_map* m) {
   cudaFree(m->md.slot_flags); cudaFree(m->md.free_stack); cudaFree(m->fs);
   cudaFree(m->words_c); cudaFree(m->coarse_list); cudaFree(m->words_f); cudaFree(m->word_off);
   cudaFree(m->partial); cudaFree(m->list_ids); cudaFree(m->list_slots); cudaFree(m->list_new);
-  cudaFree(m->list_upd); cudaFree(m->list_q); cudaFree(m->dl_sdf); cudaFree(m->dl_w); cudaFree(m->dl_col);
+  cudaFree(m->list_upd); cudaFree(m->list_q); cudaFree(m->list_setup); cudaFree(m->dl_sdf); cudaFree(m->dl_w); cudaFree(m->dl_col);
   cudaFree(m->count_d); cudaFree(m->atlas); cudaFree(m->patch_d);
   cudaFreeHost(m->res_h); cudaFreeHost(m->out_ids_h); cudaFreeHost(m->out_new_h); cudaFreeHost(m->out_upd_h);
   cudaFreeHost(m->out_q_h); cudaFreeHost(m->upd_stage_h); cudaFreeHost(m->q_stage_h);
@@ -591,7 +609,8 @@ int tf_prepare(tf_map* m, int32_t frame_index, const tf_pose* pose, const tf_cam
   CullParams cp;
   make_cull_params(m->cfg.voxel_res, m->cfg.trunc, *pose, *cam, cp);
   // pass 1: culling only, to learn the list length before anything is created
-  if (int rc = launch_cull(m, cp, m->slots[s].depth, -1)) return rc;
+  static const GroupParams kNoFrames{};
+  if (int rc = launch_cull(m, cp, kNoFrames, m->slots[s].depth, -1)) return rc;
   publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);
   if (int rc = check_kernel(m, "publish_kernel")) return rc;
   CUDA_OK(m, cudaStreamSynchronize(m->stream));
@@ -601,8 +620,8 @@ int tf_prepare(tf_map* m, int32_t frame_index, const tf_pose* pose, const tf_cam
   if (n > cap || (n > 0 && (!ids_out || !is_new_out)))
     return fail(m, TF_ERR_CAPACITY, "tf_prepare: output capacity too small");
   // pass 2: HasChunk / CreateChunk
-  alloc_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, m->md, m->fs, m->coarse_list, m->words_f, m->word_off,
-                                                    m->list_ids, m->list_slots, m->list_new, 1);
+  alloc_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, kNoFrames, m->md, m->fs, m->coarse_list, m->words_f, m->word_off,
+                                                    m->list_ids, m->list_slots, m->list_new, m->list_setup, 1);
   if (int rc = check_kernel(m, "alloc_kernel")) return rc;
   publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);
   if (int rc = check_kernel(m, "publish_kernel")) return rc;
@@ -624,7 +643,7 @@ int tf_integrate_group(tf_map* m, const tf_group_frame* frames, int32_t n_frames
   bool color[kMaxGroupFrames];
   if (int rc = build_group(m, frames, n_frames, cam, gp, color)) return rc;
   if (n == 0) return TF_OK;  // Structure/Chisel.h:228
-  if (int rc = lookup_ids(m, ids, n, true)) return rc;
+  if (int rc = lookup_ids(m, ids, n, true, &gp)) return rc;
   if (int rc = launch_integrate(m, gp, nullptr, (int)n, algorithmic_bytes(m, n, color, n_frames))) return rc;
   CUDA_OK(m, cudaMemcpyAsync(m->upd_stage_h, m->list_upd, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, m->stream));
   if (quality_out)
@@ -675,7 +694,7 @@ static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, co
   const int s = find_slot(m, frames[0].frame_index);
   CullParams cp;
   make_cull_params(m->cfg.voxel_res, m->cfg.trunc, frames[0].pose, *cam, cp);
-  if (int rc = launch_cull(m, cp, m->slots[s].depth, 1)) return rc;
+  if (int rc = launch_cull(m, cp, gp, m->slots[s].depth, 1)) return rc;
   if (int rc = launch_integrate(m, gp, &m->fs->n_list, 0, -1)) return rc;
   const int ocap = (int)std::min<int64_t>(cap, m->list_cap);
   EventPair epf;
