@@ -88,10 +88,11 @@ def load() -> C.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m texturefusion_b200.build` "
+    path = os.environ.get("TEXFUSION_B200_LIB", LIB_PATH)  # override: A/B builds of the same library
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -m texturefusion_b200.build` "
                            "(there is no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, i64 = C.c_void_p, C.c_int64
     L.tf_create.argtypes = [C.POINTER(vp), C.POINTER(Config)]
     L.tf_destroy.argtypes = [vp]
