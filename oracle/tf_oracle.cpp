@@ -669,7 +669,8 @@ int tfo_atlas_alloc_slot(tfo_map* h, int32_t x, int32_t y, int32_t z, uint64_t* 
 // resize_linear_8uc3 below and pinned against Python cv2.resize in tests/.
 static void resize_linear_8uc3(const uint8_t* src, int sstride, int sw, int sh, uint8_t* dst,
                                int dstride, int dw, int dh) {
-  const double sx = (double)sw / dw, sy = (double)sh / dh;
+  // cv::resize: inv_scale = dsize/ssize, scale = 1/inv_scale (imgproc resize.cpp)
+  const double sx = 1.0 / ((double)dw / (double)sw), sy = 1.0 / ((double)dh / (double)sh);
   std::vector<int> xo(dw), yo(dh);
   std::vector<short> xa(2 * dw), ya(2 * dh);
   auto coef = [](int dn, int sn, double scale, std::vector<int>& ofs, std::vector<short>& ab) {

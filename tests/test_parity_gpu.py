@@ -221,3 +221,107 @@ def test_fast_projection_never_disagrees_with_exact_path():
         assert not bad.any(), f"{bad.sum()} accepted fast-path results differ, e.g. c={c[bad][:3]} cz={cz[bad][:3]}"
         tot_acc += acc[: n].mean()
     assert tot_acc / 3 > 0.5  # the fast path is actually taken (engineered half declines by design)
+
+
+def _oracle_keyframe_group(o, cam, group, poses, flag, ids=None):
+    """ReIntegrateKeyframe on the oracle: group[0] is the key-frame (colour + quality), the rest
+    are its local depth frames.  flag 1: prepare/integrate/finalize; flag 0: de-integrate over ids."""
+    kf = group[0]
+    if flag == 1:
+        ids, new = o.prepare(kf.depth, poses[0], cam)
+        nu = np.zeros(len(ids), np.uint8)
+    else:
+        new = np.zeros(len(ids), np.uint8)
+        nu = np.ones(len(ids), np.uint8)
+    nu, q = o.integrate(kf.depth, kf.rgba(), kf.quality, poses[0], cam, ids, flag, kf.index, nu)
+    for lf, p in zip(group[1:], poses[1:]):
+        nu, _ = o.integrate(lf.depth, None, None, p, cam, ids, flag, -1, nu)
+    valid = o.finalize(ids, nu, new)
+    keep = nu != 0
+    return valid, q[keep]
+
+
+@pytest.mark.parametrize("res", (0.02, 0.005))
+def test_batch_loop_closure_reintegration(res):
+    """tf_integrate_batch: key-frame groups fused under drifted poses, then every key-frame is
+    de-integrated (old poses, its validChunks) and re-integrated (corrected poses) — the loop of
+    GCFusion/MobileFusion.cpp:301-310, batched."""
+    from texturefusion_b200 import synth
+    cam = synth.Camera()
+    seq = synth.make_sequence(9, cam=cam, total=300, keyframe_every=3, with_drift=True, start=60)
+    groups = [seq.frames[k:k + 3] for k in range(0, 9, 3)]
+    g = capi.Map(res, max_frames=16)
+    o = OracleMap(res)
+    for fr in seq.frames:
+        g.upload_frame(fr.index, fr.depth, fr.rgba() if fr.is_keyframe else None, fr.quality if fr.is_keyframe else None)
+
+    def item(group, flag, old, ids=None):
+        d = {"flag": flag, "frames": [(fr.index, k == 0, fr.pose_old if old else fr.pose) for k, fr in enumerate(group)]}
+        if ids is not None:
+            d["ids"] = ids
+        return d
+
+    # 1. first fusion under the drifted poses
+    res1 = g.integrate_batch([item(gr, 1, True) for gr in groups], cam)
+    valid_lists = []
+    for gr, (gv, gq) in zip(groups, res1):
+        ov, oq = _oracle_keyframe_group(o, cam, gr, [fr.pose_old for fr in gr], 1)
+        assert np.array_equal(gv, ov)
+        assert np.array_equal(gq.view(np.uint32), oq.view(np.uint32))
+        valid_lists.append(ov)
+    assert assert_maps_equal(g, o, what="batch: first fusion")
+    # 2. loop closure: de-integrate + re-integrate every key-frame in one batch call
+    items = []
+    for gr, vl in zip(groups, valid_lists):
+        items += [item(gr, 0, True, vl), item(gr, 1, False)]
+    res2 = g.integrate_batch(items, cam)
+    for k, (gr, vl) in enumerate(zip(groups, valid_lists)):
+        _oracle_keyframe_group(o, cam, gr, [fr.pose_old for fr in gr], 0, vl)
+        ov, oq = _oracle_keyframe_group(o, cam, gr, [fr.pose for fr in gr], 1)
+        gv, gq = res2[2 * k + 1]
+        assert np.array_equal(gv, ov)
+        assert np.array_equal(gq.view(np.uint32), oq.view(np.uint32))
+    assert assert_maps_equal(g, o, what="batch: after loop closure")
+
+
+@pytest.mark.parametrize("res,n_ranks", ((0.02, 2), (0.005, 4)))
+def test_sharded_maps_union_equals_single_map(res, n_ranks):
+    """Chunk sharding (one tf_map per rank): every rank culls the same broadcast frame and keeps the
+    chunks it owns; the union of the per-rank maps is the single-GPU map, and the merged
+    per-rank lists restore the reference's traversal order."""
+    from texturefusion_b200 import sharding
+    seq = room_sequence(4)
+    cam = seq.cam
+    single = capi.Map(res)
+    ranks = [capi.Map(res, n_ranks=n_ranks, rank=r, max_chunks=1 << 16) for r in range(n_ranks)]
+    o = OracleMap(res)
+    for fr in seq.frames:
+        rgba = fr.rgba() if fr.is_keyframe else None
+        q = fr.quality if fr.is_keyframe else None
+        single.upload_frame(fr.index, fr.depth, rgba, q)
+        st, ids, new, upd, qs = single.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam)
+        lo, _ = o.boundary_ids(fr.depth, fr.pose, cam)
+        parts, pay = [], []
+        for r, m in enumerate(ranks):
+            m.upload_frame(fr.index, fr.depth, rgba, q)
+            st_r, ids_r, new_r, upd_r, q_r = m.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam)
+            assert np.all(sharding.owner_of(ids_r, n_ranks) == r)
+            parts.append(ids_r)
+            pay.append((new_r, upd_r, q_r))
+        step = 1 if np.float32(res) > 0.01 else 4
+        m_ids, m_new, m_upd, m_q = sharding.merge_rank_lists(parts, pay, min_id=lo, step=step)
+        assert np.array_equal(m_ids, ids) and np.array_equal(m_new, new) and np.array_equal(m_upd, upd)
+        assert np.array_equal(m_q.view(np.uint32), qs.view(np.uint32))
+    all_ids = np.concatenate([m.list_chunks() for m in ranks])
+    assert len(all_ids) == single.chunk_count() and sum(m.chunk_count() for m in ranks) == single.chunk_count()
+    si, _ = sort_ids(single.list_chunks())
+    ai, order = sort_ids(all_ids)
+    assert np.array_equal(si, ai)
+    ss, sw, sc = single.download_chunks(si)
+    for r, m in enumerate(ranks):
+        mine = si[sharding.owner_of(si, n_ranks) == r]
+        rs, rw, rc = m.download_chunks(mine)
+        sel = sharding.owner_of(si, n_ranks) == r
+        assert np.array_equal(rs.view(np.uint32), ss[sel].view(np.uint32))
+        assert np.array_equal(rw.view(np.uint32), sw[sel].view(np.uint32))
+        assert np.array_equal(rc, sc[sel])
