@@ -243,6 +243,10 @@ def main():
     c1 = m.counters()
     dev_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b))
     dev_ms = max_over_ranks(dev_ms)
+    if dist is not None:  # whole-job totals: every rank fused its own share of the chunks
+        tot = torch.tensor([float(vox), float(chunks)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot)
+        vox, chunks = int(tot[0].item()), int(tot[1].item())
     launches = c1["kernel_launches"] - c0["kernel_launches"]
     value = args.steps / (dev_ms * 1e-3)
     live_chunks = m.chunk_count()
