@@ -230,7 +230,7 @@ void* tf_stream(tf_map* m);
  * measured with CUDA events on the map's stream when enabled via tf_set_profiling. */
 int tf_set_profiling(tf_map* m, int level /* 0 off, 1 integrate kernel, 2 every pipeline stage */);
 /* device time (ms) per stage of the fused pipeline since the last reset, level 2 only:
- * [bbox, cull_coarse, cull_fine, alloc, integrate, finalize] */
+ * [bbox, cull, -, alloc, integrate (+ fused finalize), -] */
 int tf_get_stage_times(tf_map* m, int reset, double* ms6);
 int tf_get_kernel_time(tf_map* m, int reset, double* integrate_ms, int64_t* integrate_launches,
                        double* integrate_bytes);

@@ -406,7 +406,8 @@ class Map:
     def stage_times(self, reset=True) -> dict:
         arr = (C.c_double * 6)()
         self._check(self.L.tf_get_stage_times(self.h, int(reset), arr))
-        return dict(zip(("bbox", "cull_coarse", "cull_fine", "alloc", "integrate", "finalize"), arr))
+        t = dict(zip(("bbox", "cull", "_2", "alloc", "integrate+finalize", "_5"), arr))
+        return {k: v for k, v in t.items() if not k.startswith("_")}
 
     def kernel_time(self, reset=True):
         ms, n, b = C.c_double(), C.c_int64(), C.c_double()

@@ -38,7 +38,7 @@ struct FrameSlot {
 struct EventPair {
   cudaEvent_t a, b;
   double bytes;
-  int stage;  // 0 bbox, 1 coarse, 2 fine, 3 alloc, 4 integrate, 5 finalize
+  int stage;  // 0 bbox, 1 cull, 2 (unused), 3 alloc, 4 integrate (+ fused finalize), 5 (unused)
 };
 constexpr int kStages = 6;
 
@@ -49,18 +49,19 @@ struct tf_map {
   int W = 0, H = 0, npix = 0;
   cudaStream_t stream = nullptr;
   std::string err;
-  int sm_count = 0, grid = 0, grid_integrate = 0, grid_integrate_c = 0;
+  int sm_count = 0, grid = 0, grid_cull = 0, grid_integrate = 0, grid_integrate_c = 0;
 
   MapDev md{};
   FrameState* fs = nullptr;
   int hash_cap = 0;
 
   // per-frame scratch
-  int cand_cap = 0, fine_words_cap = 0, list_cap = 0;
-  unsigned* words_c = nullptr;
-  int* coarse_list = nullptr;
-  unsigned* words_f = nullptr;
-  int* word_off = nullptr;
+  int cand_cap = 0, list_cap = 0;
+  unsigned long long* child_mask = nullptr;  // per coarse candidate: which of its children are hit
+  int* local_off = nullptr;                  // exclusive hit count inside the candidate's 32-candidate word
+  int* hit_cands = nullptr;
+  unsigned char* hit_count = nullptr;  // fine hits per coarse candidate (<= 64)
+  int* word_base = nullptr;
   float* partial = nullptr;
   int3* list_ids = nullptr;
   int* list_slots = nullptr;
@@ -264,35 +265,34 @@ int launch_cull(tf_map* m, const CullParams& cp, const GroupParams& gp, const fl
   bbox_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->partial, m->cand_cap);
   if (st) { prof_end(m, ep, 0); prof_begin(m, ep); }
   if (int rc = check_kernel(m, "bbox_kernel")) return rc;
-  cull_coarse_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->words_c, m->coarse_list,
-                                                          m->fine_words_cap);
-  if (st) { prof_end(m, ep, 1); prof_begin(m, ep); }
-  if (int rc = check_kernel(m, "cull_coarse_kernel")) return rc;
-  cull_fine_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->coarse_list, m->words_f, m->word_off,
-                                                        m->cfg.n_ranks, m->cfg.rank, m->list_cap);
-  if (st) prof_end(m, ep, 2);
-  if (int rc = check_kernel(m, "cull_fine_kernel")) return rc;
+  cull_kernel<<<m->grid_cull, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->child_mask, m->hit_count, m->local_off, m->word_base,
+                                                        m->hit_cands, m->cfg.n_ranks, m->cfg.rank, m->list_cap);
+  if (st) prof_end(m, ep, 1);
+  if (int rc = check_kernel(m, "cull_kernel")) return rc;
   if (do_alloc >= 0) {
     if (st) prof_begin(m, ep);
-    alloc_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, gp, m->md, m->fs, m->coarse_list, m->words_f, m->word_off,
-                                                      m->list_ids, m->list_slots, m->list_new, m->list_setup, do_alloc);
+    alloc_kernel<<<m->grid_cull, kThreads, 0, m->stream>>>(cp, gp, m->md, m->fs, m->child_mask, m->local_off, m->word_base,
+                                                      m->hit_cands, m->list_ids, m->list_slots, m->list_new, m->list_setup, do_alloc);
     if (st) prof_end(m, ep, 3);
     if (int rc = check_kernel(m, "alloc_kernel")) return rc;
   }
   return TF_OK;
 }
 
-int launch_integrate(tf_map* m, const GroupParams& gp, const int* n_dev, int n_host, double bytes) {
+int launch_integrate(tf_map* m, const GroupParams& gp, const int* n_dev, int n_host, double bytes,
+                     const FusedFinalize* fused = nullptr) {
+  FusedFinalize ff{};
+  if (fused) ff = *fused;
   EventPair ep;
   if (m->prof) prof_begin(m, ep);
   bool any_color = false;
   for (int f = 0; f < gp.n_frames; f++) any_color |= gp.f[f].rgba != nullptr;
   if (any_color)
     integrate_kernel<true><<<m->grid_integrate_c, kThreads, integrate_smem_bytes(gp.n_frames), m->stream>>>(
-        gp, m->md, m->list_slots, m->list_setup, n_dev, n_host, m->list_upd, m->list_q);
+        gp, m->md, m->list_slots, m->list_setup, n_dev, n_host, m->list_upd, m->list_q, ff);
   else
     integrate_kernel<false><<<m->grid_integrate, kThreads, integrate_smem_bytes(gp.n_frames), m->stream>>>(
-        gp, m->md, m->list_slots, m->list_setup, n_dev, n_host, m->list_upd, m->list_q);
+        gp, m->md, m->list_slots, m->list_setup, n_dev, n_host, m->list_upd, m->list_q, ff);
   if (m->prof) {
     prof_end(m, ep);
     m->ev_pending.back().bytes = bytes;
@@ -368,7 +368,7 @@ void tf_destroy(tf_map* m) {
   if (m->stream) cudaStreamSynchronize(m->stream);
   cudaFree(m->md.keys); cudaFree(m->md.vals); cudaFree(m->md.pool); cudaFree(m->md.slot_id);
   cudaFree(m->md.slot_flags); cudaFree(m->md.free_stack); cudaFree(m->fs);
-  cudaFree(m->words_c); cudaFree(m->coarse_list); cudaFree(m->words_f); cudaFree(m->word_off);
+  cudaFree(m->child_mask); cudaFree(m->local_off); cudaFree(m->hit_cands); cudaFree(m->hit_count); cudaFree(m->word_base);
   cudaFree(m->partial); cudaFree(m->list_ids); cudaFree(m->list_slots); cudaFree(m->list_new);
   cudaFree(m->list_upd); cudaFree(m->list_q); cudaFree(m->list_setup); cudaFree(m->dl_sdf); cudaFree(m->dl_w); cudaFree(m->dl_col);
   cudaFree(m->count_d); cudaFree(m->atlas); cudaFree(m->patch_d);
@@ -452,6 +452,7 @@ int tf_create(tf_map** out, const tf_config* cfg) {
   C_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, integrate_kernel<true>, kThreads, integrate_smem_bytes(1)));
   m->grid_integrate_c = m->sm_count * std::max(1, occ_c);
   m->grid = m->sm_count * 2;
+  m->grid_cull = m->sm_count * 4;
   m->grid_integrate = m->sm_count * std::max(1, occ);
 
   const int64_t max_chunks = cfg->max_chunks > 0 ? cfg->max_chunks : (int64_t)1 << 19;
@@ -471,13 +472,13 @@ int tf_create(tf_map** out, const tf_config* cfg) {
   C_OK(dmalloc(&m->md.free_stack, (size_t)max_chunks));
   C_OK(dmalloc(&m->fs, 1));
 
-  m->cand_cap = 1 << 23;
-  m->fine_words_cap = 1 << 20;
+  m->cand_cap = 1 << 22;  // coarse candidates per frame (4^3-chunk blocks at <= 10 mm voxels)
   m->list_cap = 1 << 19;
-  C_OK(dmalloc(&m->words_c, (size_t)m->cand_cap / 32));
-  C_OK(dmalloc(&m->coarse_list, (size_t)m->cand_cap));
-  C_OK(dmalloc(&m->words_f, (size_t)m->fine_words_cap));
-  C_OK(dmalloc(&m->word_off, (size_t)m->fine_words_cap));
+  C_OK(dmalloc(&m->child_mask, (size_t)m->cand_cap));
+  C_OK(dmalloc(&m->local_off, (size_t)m->cand_cap));
+  C_OK(dmalloc(&m->hit_cands, (size_t)m->cand_cap));
+  C_OK(dmalloc(&m->hit_count, (size_t)m->cand_cap + 32));
+  C_OK(dmalloc(&m->word_base, (size_t)m->cand_cap / 32));
   C_OK(dmalloc(&m->partial, (size_t)m->grid * 6));
   C_OK(dmalloc(&m->list_ids, (size_t)m->list_cap));
   C_OK(dmalloc(&m->list_slots, (size_t)m->list_cap));
@@ -620,8 +621,8 @@ int tf_prepare(tf_map* m, int32_t frame_index, const tf_pose* pose, const tf_cam
   if (n > cap || (n > 0 && (!ids_out || !is_new_out)))
     return fail(m, TF_ERR_CAPACITY, "tf_prepare: output capacity too small");
   // pass 2: HasChunk / CreateChunk
-  alloc_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, kNoFrames, m->md, m->fs, m->coarse_list, m->words_f, m->word_off,
-                                                    m->list_ids, m->list_slots, m->list_new, m->list_setup, 1);
+  alloc_kernel<<<m->grid_cull, kThreads, 0, m->stream>>>(cp, kNoFrames, m->md, m->fs, m->child_mask, m->local_off, m->word_base,
+                                                    m->hit_cands, m->list_ids, m->list_slots, m->list_new, m->list_setup, 1);
   if (int rc = check_kernel(m, "alloc_kernel")) return rc;
   publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);
   if (int rc = check_kernel(m, "publish_kernel")) return rc;
@@ -695,16 +696,20 @@ static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, co
   CullParams cp;
   make_cull_params(m->cfg.voxel_res, m->cfg.trunc, frames[0].pose, *cam, cp);
   if (int rc = launch_cull(m, cp, gp, m->slots[s].depth, 1)) return rc;
-  if (int rc = launch_integrate(m, gp, &m->fs->n_list, 0, -1)) return rc;
   const int ocap = (int)std::min<int64_t>(cap, m->list_cap);
-  EventPair epf;
-  if (m->prof >= 2) prof_begin(m, epf);
-  finalize_kernel<<<m->grid, kThreads, 0, m->stream>>>(
-      m->md, m->fs, m->list_ids, m->list_slots, m->list_new, m->list_upd, m->list_q, 1,
-      ids_out ? m->out_ids_d : nullptr, new_out ? m->out_new_d : nullptr, upd_out ? m->out_upd_d : nullptr,
-      q_out ? m->out_q_d : nullptr, ocap, m->res_d);
-  if (m->prof >= 2) prof_end(m, epf, 5);
-  if (int rc = check_kernel(m, "finalize_kernel")) return rc;
+  FusedFinalize ff{};
+  ff.enabled = 1;
+  ff.fs = m->fs;
+  ff.list_ids = m->list_ids;
+  ff.list_new = m->list_new;
+  ff.ids_out = ids_out ? m->out_ids_d : nullptr;
+  ff.new_out = new_out ? m->out_new_d : nullptr;
+  ff.upd_out = upd_out ? m->out_upd_d : nullptr;
+  ff.q_out = q_out ? m->out_q_d : nullptr;
+  ff.out_cap = ocap;
+  ff.res = m->res_d;
+  // integrate + Finalize (flags, garbage collection, result publication) in one kernel
+  if (int rc = launch_integrate(m, gp, &m->fs->n_list, 0, -1, &ff)) return rc;
   CUDA_OK(m, cudaStreamSynchronize(m->stream));
   absorb_result(m);
   const FrameResultHost r = *m->res_h;
