@@ -139,6 +139,23 @@ cudaError_t dmalloc(T** p, size_t n) {
   return cudaMalloc((void**)p, n * sizeof(T));
 }
 
+// Launch with programmatic stream serialization: the kernel may start while its predecessor on
+// the stream is still running and synchronises with it through griddepcontrol.wait.
+template <class... KArgs, class... Args>
+void launch_pdl(void (*kernel)(KArgs...), int grid, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 int check_kernel(tf_map* m, const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(m, TF_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -265,14 +282,15 @@ int launch_cull(tf_map* m, const CullParams& cp, const GroupParams& gp, const fl
   bbox_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->partial, m->cand_cap);
   if (st) { prof_end(m, ep, 0); prof_begin(m, ep); }
   if (int rc = check_kernel(m, "bbox_kernel")) return rc;
-  cull_kernel<<<m->grid_cull, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->child_mask, m->hit_count, m->local_off, m->word_base,
-                                                        m->hit_cands, m->cfg.n_ranks, m->cfg.rank, m->list_cap);
+  launch_pdl(cull_kernel, m->grid_cull, 0, m->stream, cp, depth, m->fs, m->child_mask, m->hit_count, m->local_off,
+             m->word_base, m->hit_cands, m->cfg.n_ranks, m->cfg.rank, m->list_cap);
   if (st) prof_end(m, ep, 1);
   if (int rc = check_kernel(m, "cull_kernel")) return rc;
   if (do_alloc >= 0) {
     if (st) prof_begin(m, ep);
-    alloc_kernel<<<m->grid_cull, kThreads, 0, m->stream>>>(cp, gp, m->md, m->fs, m->child_mask, m->local_off, m->word_base,
-                                                      m->hit_cands, m->list_ids, m->list_slots, m->list_new, m->list_setup, do_alloc);
+    launch_pdl(alloc_kernel, m->grid_cull, 0, m->stream, cp, gp, m->md, m->fs, (const unsigned long long*)m->child_mask,
+               (const int*)m->local_off, (const int*)m->word_base, (const int*)m->hit_cands, m->list_ids, m->list_slots,
+               m->list_new, m->list_setup, do_alloc);
     if (st) prof_end(m, ep, 3);
     if (int rc = check_kernel(m, "alloc_kernel")) return rc;
   }
@@ -288,11 +306,11 @@ int launch_integrate(tf_map* m, const GroupParams& gp, const int* n_dev, int n_h
   bool any_color = false;
   for (int f = 0; f < gp.n_frames; f++) any_color |= gp.f[f].rgba != nullptr;
   if (any_color)
-    integrate_kernel<true><<<m->grid_integrate_c, kThreads, integrate_smem_bytes(gp.n_frames), m->stream>>>(
-        gp, m->md, m->list_slots, m->list_setup, n_dev, n_host, m->list_upd, m->list_q, ff);
+    launch_pdl(integrate_kernel<true>, m->grid_integrate_c, integrate_smem_bytes(gp.n_frames), m->stream, gp, m->md,
+               (const int*)m->list_slots, (const float*)m->list_setup, n_dev, n_host, m->list_upd, m->list_q, ff);
   else
-    integrate_kernel<false><<<m->grid_integrate, kThreads, integrate_smem_bytes(gp.n_frames), m->stream>>>(
-        gp, m->md, m->list_slots, m->list_setup, n_dev, n_host, m->list_upd, m->list_q, ff);
+    launch_pdl(integrate_kernel<false>, m->grid_integrate, integrate_smem_bytes(gp.n_frames), m->stream, gp, m->md,
+               (const int*)m->list_slots, (const float*)m->list_setup, n_dev, n_host, m->list_upd, m->list_q, ff);
   if (m->prof) {
     prof_end(m, ep);
     m->ev_pending.back().bytes = bytes;
