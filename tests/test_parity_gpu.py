@@ -325,3 +325,58 @@ def test_sharded_maps_union_equals_single_map(res, n_ranks):
         assert np.array_equal(rs.view(np.uint32), ss[sel].view(np.uint32))
         assert np.array_equal(rw.view(np.uint32), sw[sel].view(np.uint32))
         assert np.array_equal(rc, sc[sel])
+
+
+def test_capacity_errors_and_frame_store_eviction():
+    """Pool exhaustion is reported (TF_ERR_CAPACITY), not silently dropped; the frame store
+    replaces its least-recently-used slot."""
+    seq = room_sequence(4)
+    cam = seq.cam
+    fr = seq.frames[0]
+    tiny = capi.Map(0.005, max_chunks=1024, max_frames=2)
+    tiny.upload_frame(fr.index, fr.depth)
+    with pytest.raises(capi.TexFusionError) as e:
+        tiny.integrate_frame(fr.index, False, fr.pose, cam)
+    assert e.value.code == capi.TF_ERR_CAPACITY and "pool" in str(e.value)
+    # LRU: with two slots, uploading a third frame evicts the oldest one
+    g = capi.Map(0.02, max_frames=2)
+    for f in seq.frames[:3]:
+        g.upload_frame(f.index, f.depth)
+    with pytest.raises(capi.TexFusionError) as e:
+        g.prepare(seq.frames[0].index, seq.frames[0].pose, cam)
+    assert e.value.code == capi.TF_ERR_NOT_FOUND
+    ids, _ = g.prepare(seq.frames[2].index, seq.frames[2].pose, cam)
+    assert len(ids) > 0
+    g.release_frame(seq.frames[2].index)
+    with pytest.raises(capi.TexFusionError):
+        g.prepare(seq.frames[2].index, seq.frames[2].pose, cam)
+    # output capacity: the two-call pattern of tf_prepare
+    g.upload_frame(5, fr.depth)
+    with pytest.raises(capi.TexFusionError) as e:
+        g.prepare(5, fr.pose, cam, cap=10)
+    assert e.value.code == capi.TF_ERR_CAPACITY and g.chunk_count() == len(ids)  # nothing was created
+    # wrong image size
+    from texturefusion_b200 import synth
+    with pytest.raises(capi.TexFusionError):
+        g.prepare(5, fr.pose, synth.Camera().scaled(0.5))
+
+
+def test_long_sequence_chunk_recycling():
+    """60 frames at 5 mm: thousands of chunks are created and garbage-collected every frame, so
+    slots and hash tombstones are recycled many times; the map must still equal the oracle's."""
+    seq = room_sequence(60, keyframe_every=10)
+    cam = seq.cam
+    g = capi.Map(0.005, max_chunks=1 << 17)
+    o = OracleMap(0.005, threads=0)
+    removed = 0
+    for fr in seq.frames:
+        rgba = fr.rgba() if fr.is_keyframe else None
+        g.upload_frame(fr.index, fr.depth, rgba, fr.quality if fr.is_keyframe else None)
+        st, *_ = g.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam, want_lists=False)
+        n, nupd = o.integrate_frame(fr.depth, rgba, fr.quality, fr.pose, cam, -1)
+        assert (st.n_chunks, st.n_updated) == (n, nupd)
+        removed += st.n_removed
+    assert removed > 50000
+    assert assert_maps_equal(g, o, what="60-frame sequence")
+    c = g.counters()
+    assert c["pool_used"] == g.chunk_count() and c["frames_integrated"] == 60
