@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -148,11 +149,13 @@ void launch_pdl(void (*kernel)(KArgs...), int grid, size_t smem, cudaStream_t st
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
+  // on by default; TEXFUSION_B200_PDL=0 falls back to plain stream order
+  static const bool use_pdl = [] { const char* e = getenv("TEXFUSION_B200_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = use_pdl ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
