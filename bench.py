@@ -46,6 +46,17 @@ def load_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one captured integrate_kernel launch
+    (ncu --set full; profiles/r1_integrate_traffic.json), or None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r1_integrate_traffic.json")
+    try:
+        d = json.load(open(p))
+        return float(d["dram_bytes_per_launch"]), d["note"]
+    except Exception:
+        return None, "no ncu capture committed"
+
+
 class ClockSampler:
     """Samples nvidia-smi SM clocks and throttle reasons during the timed region."""
 
@@ -275,8 +286,9 @@ def main():
     stage_us = {k: 1e3 * v / args.steps for k, v in m.stage_times().items()}
     m.close()
     achieved = (k_bytes / 1e9) / (k_ms * 1e-3) if k_ms > 0 else 0.0
+    traffic, traffic_note = load_traffic()
     roofline = {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak_gbs, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                 "launches": k_n, "avg_launch_us": 1e3 * k_ms / max(k_n, 1),
                 "algorithmic_bytes_per_launch": k_bytes / max(k_n, 1),
                 "kernel_share_of_step": k_ms / dev_ms if dev_ms > 0 else None}

@@ -213,6 +213,18 @@ int tf_atlas_update(tf_map* m, const tf_patch_desc* patches, int64_t n);
 int tf_atlas_download(tf_map* m, uint64_t hot_start, uint64_t hot_end, uint8_t* rgb_out);
 int tf_atlas_patch_size(tf_map* m, int32_t* patch_w, int32_t* patch_h);
 
+/* Patch::CalculateTexCoords (Structure/Patch.cpp:40-108, bilinear :110-146, bilinear_depth
+ * :148-170) for a batch of chunk meshes against key-frame frame_index (its rgb and depth must be
+ * in the store).  world_to_camera = pose_sophus[0].inverse().matrix().cast<float>() (:51).
+ * Patch p owns vertices [vertex_offsets[p], vertex_offsets[p+1]); vertices / colors are xyz / rgb
+ * float triples (mesh->vertices, mesh->colors).  Outputs: texcoord (2 floats per vertex, already
+ * shifted by the bounding box like :101-103), texcolor (3 floats), and per patch the bounding box
+ * (cv::Rect), wrong_mapping (:87-96) and the return flag (-1 if a vertex left the image). */
+typedef struct { int32_t x, y, w, h; int32_t wrong_mapping; int32_t flag; } tf_patch_result;
+int tf_patch_texcoords(tf_map* m, int32_t frame_index, const tf_pose* world_to_camera, const tf_camera* cam,
+                       int64_t n_patches, const int64_t* vertex_offsets, const float* vertices,
+                       const float* colors, float* texcoord_out, float* texcolor_out, tf_patch_result* results);
+
 /* ---- misc ---------------------------------------------------------------------------- */
 int tf_sync(tf_map* m);
 /* counters since creation: kernels launched by this library, bytes moved each way */

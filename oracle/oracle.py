@@ -68,6 +68,7 @@ def _lib():
         L.tfo_atlas_alloc_slot.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]
         L.tfo_atlas_update.argtypes = [vp, C.c_uint64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.tfo_atlas_download.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
+        L.tfo_patch_texcoords.argtypes = [vp, vp, vp, C.POINTER(_Cam), C.c_int64, vp, vp, vp, vp, vp, vp]
         L.tfo_truncation_distance.restype = C.c_float
         L.tfo_truncation_distance.argtypes = [f32p, C.c_float]
         L.tfo_centroids.argtypes = [vp, vp, vp]
@@ -91,6 +92,22 @@ def _cam(cam) -> _Cam:
 def truncation_distance(z: float, trunc=DEFAULT_TRUNC) -> float:
     t = (C.c_float * 5)(*trunc)
     return float(_lib().tfo_truncation_distance(t, C.c_float(z)))
+
+
+def patch_texcoords(rgb, depth, world_to_camera, cam, offsets, vertices, colors):
+    """Patch::CalculateTexCoords (Structure/Patch.cpp:40-108) for a batch of meshes on the CPU."""
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    d = np.ascontiguousarray(depth, np.float32)
+    off = np.ascontiguousarray(offsets, np.int64)
+    v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+    c = np.ascontiguousarray(colors, np.float32).reshape(-1, 3)
+    n = len(off) - 1
+    tc = np.empty((len(v), 2), np.float32)
+    col = np.empty((len(v), 3), np.float32)
+    res = np.empty((max(n, 1), 6), np.int32)
+    _lib().tfo_patch_texcoords(_p(rgb), _p(d), _p(_pose(world_to_camera)), C.byref(_cam(cam)), n, _p(off), _p(v), _p(c),
+                               _p(tc), _p(col), _p(res))
+    return tc, col, res[:n]
 
 
 class OracleMap:

@@ -740,6 +740,110 @@ int tfo_atlas_download(tfo_map* h, uint64_t hot_start, uint64_t hot_end, uint8_t
   return 0;
 }
 
+// ---- Patch::CalculateTexCoords — Structure/Patch.cpp:40-108 (+ bilinear :110-146, bilinear_depth :148-170)
+struct PatchResult { int32_t x, y, w, h, wrong_mapping, flag; };
+
+// cv::Mat::at beyond the last column reads the next row (contiguous image); beyond the buffer -> 0
+static inline float px(const uint8_t* rgb, int W, int H, int y, int x, int c) {
+  const long idx = (long)y * W + x;
+  return (idx >= 0 && idx < (long)W * H) ? (float)rgb[idx * 3 + c] : 0.0f;
+}
+static inline float dp(const float* d, int W, int H, int y, int x) {
+  const long idx = (long)y * W + x;
+  return (idx >= 0 && idx < (long)W * H) ? d[idx] : 0.0f;
+}
+static void bilinear_rgb(const uint8_t* rgb, int W, int H, float lx, float ly, float out[3]) {
+  const int x = (int)std::floor(lx), y = (int)std::floor(ly);
+  for (int c = 0; c < 3; c++) {
+    if (x < W - 1 && y < H - 1) {
+      const float c1 = px(rgb, W, H, y, x, c), c2 = px(rgb, W, H, y, x + 1, c), c3 = px(rgb, W, H, y + 1, x, c);
+      // (the reference uses c2 where c4 is meant, Patch.cpp:125-128)
+      out[c] = c1 * (x + 1 - lx) * (y + 1 - ly) + c2 * (lx - x) * (y + 1 - ly) + c3 * (x + 1 - lx) * (ly - y) +
+               c2 * (lx - x) * (ly - y);
+    } else if (x < W - 1 && y == H - 1) {
+      out[c] = px(rgb, W, H, y, x, c) * (x + 1 - lx) + px(rgb, W, H, y, x + 1, c) * (lx - x);
+    } else if (x == W - 1 && y < H - 1) {
+      out[c] = px(rgb, W, H, y, x, c) * (y + 1 - ly) + px(rgb, W, H, y + 1, x, c) * (ly - y);
+    } else {
+      out[c] = px(rgb, W, H, y, x, c);
+    }
+  }
+}
+static float bilinear_d(const float* d, int W, int H, float lx, float ly) {
+  const int x = (int)std::floor(lx), y = (int)std::floor(ly);
+  if (x < W - 1 && y < H - 1) {
+    const float c1 = dp(d, W, H, y, x), c2 = dp(d, W, H, y, x + 1), c3 = dp(d, W, H, y + 1, x);
+    return c1 * (x + 1 - lx) * (y + 1 - ly) + c2 * (lx - x) * (y + 1 - ly) + c3 * (x + 1 - lx) * (ly - y) +
+           c2 * (lx - x) * (ly - y);
+  } else if (x < W - 1 && y == H - 1) {
+    return dp(d, W, H, y, x) * (x + 1 - lx) + dp(d, W, H, y, x + 1) * (lx - x);
+  } else if (x == W - 1 && y < H - 1) {
+    return dp(d, W, H, y, x) * (y + 1 - ly) + dp(d, W, H, y + 1, x) * (ly - y);
+  }
+  return dp(d, W, H, y, x);
+}
+
+// T: world->camera 4x4 (column-major), i.e. pose_sophus[0].inverse().matrix().cast<float>()
+int tfo_patch_texcoords(const uint8_t* rgb, const float* depth, const float* T, const Cam* cam, int64_t n_patches,
+                        const int64_t* offsets, const float* verts, const float* colors, float* texcoord,
+                        float* texcolor, PatchResult* results) {
+  const int W = cam->width, H = cam->height;
+  const Intr in = truncated(*cam);
+  for (int64_t p = 0; p < n_patches; p++) {
+    const int64_t a = offsets[p], b = offsets[p + 1], n = b - a;
+    float minX = (float)W, maxX = 0.0f, minY = (float)H, maxY = 0.0f;
+    int flag = 0, depth_compare = 0, color_compare = 0;
+    for (int64_t i = a; i < b; i++) {
+      const float vx = verts[3 * i], vy = verts[3 * i + 1], vz = verts[3 * i + 2];
+      float vl[3];
+      // Matrix4f * Vector4f (packet evaluation): ((m0*x + m1*y) + m2*z) + m3*1
+      for (int k = 0; k < 3; k++) vl[k] = ((T[k] * vx + T[4 + k] * vy) + T[8 + k] * vz) + T[12 + k] * 1.0f;
+      const float dist = vl[2];
+      const float x = vl[0] / vl[2], y = vl[1] / vl[2];
+      float cameraX = x * in.fx + in.cx + 0.5;  // float*int + int, then + 0.5 in double
+      float cameraY = y * in.fy + in.cy + 0.5;
+      if (cameraX < 0 || cameraX >= W || cameraY < 0 || cameraY >= H) flag = -1;
+      if (cameraX < 0) cameraX = 0;
+      if (cameraX >= W) cameraX = W;
+      if (cameraY < 0) cameraY = 0;
+      if (cameraY >= H) cameraY = H;
+      texcoord[2 * i] = cameraX;
+      texcoord[2 * i + 1] = cameraY;
+      minX = minX < cameraX ? minX : cameraX;
+      maxX = maxX > cameraX ? maxX : cameraX;
+      minY = minY < cameraY ? minY : cameraY;
+      maxY = maxY > cameraY ? maxY : cameraY;
+      float tc[3];
+      bilinear_rgb(rgb, W, H, cameraX, cameraY, tc);
+      for (int c = 0; c < 3; c++) tc[c] = tc[c] / 255.0f;
+      for (int c = 0; c < 3; c++) texcolor[3 * i + c] = tc[c];
+      const float dd = bilinear_d(depth, W, H, cameraX, cameraY);
+      const float e0 = tc[0] - colors[3 * i], e1 = tc[1] - colors[3 * i + 1], e2 = tc[2] - colors[3 * i + 2];
+      const float nrm = std::sqrt(e0 * e0 + (e1 * e1 + e2 * e2));
+      if (nrm > 0.6) color_compare++;
+      if (std::fabs(dist - dd) > 0.7) depth_compare++;
+    }
+    PatchResult& r = results[p];
+    r.wrong_mapping = (depth_compare > 0.3 * n || color_compare > 0.3 * n) ? 1 : 0;
+    r.flag = flag;
+    if (maxX >= minX && maxY >= minY) {
+      // cv::Rect(float...) truncates towards zero; & = intersection (empty -> all zero)
+      int bx = (int)(minX - 2), by = (int)(minY - 2), bw = (int)(maxX - minX + 5), bh = (int)(maxY - minY + 5);
+      const int x1 = std::max(bx, 0), y1 = std::max(by, 0);
+      const int x2 = std::min(bx + bw, 0 + W - 1), y2 = std::min(by + bh, 0 + H - 1);
+      if (x2 - x1 <= 0 || y2 - y1 <= 0) { r.x = r.y = r.w = r.h = 0; }
+      else { r.x = x1; r.y = y1; r.w = x2 - x1; r.h = y2 - y1; }
+      for (int64_t i = a; i < b; i++) {
+        texcoord[2 * i] -= (float)r.x;
+        texcoord[2 * i + 1] -= (float)r.y;
+      }
+    } else {
+      r.x = r.y = r.w = r.h = 0;
+    }
+  }
+  return 0;
+}
+
 // expose the scalar helpers for unit tests
 float tfo_truncation_distance(const float* trunc5, float z) {
   return truncation_distance(Trunc{trunc5[0], trunc5[1], trunc5[2], trunc5[3], trunc5[4]}, z);

@@ -380,3 +380,32 @@ def test_long_sequence_chunk_recycling():
     assert assert_maps_equal(g, o, what="60-frame sequence")
     c = g.counters()
     assert c["pool_used"] == g.chunk_count() and c["frames_integrated"] == 60
+
+
+def test_full_size_round_trip_properties():
+    """Size-independent properties at the headline configuration (640x480, 5 mm):
+    integrate followed by de-integrate of the same frame under the same pose returns every
+    touched voxel to (999, 0) and every colour voxel to 0 (u16 wrap-around arithmetic);
+    integrating twice doubles the weights exactly; lists are duplicate free and owned once."""
+    seq = room_sequence(2)
+    cam = seq.cam
+    kf = seq.frames[0]
+    g = capi.Map(0.005)
+    g.upload_frame(kf.index, kf.depth, kf.rgba(), kf.quality)
+    ids, new = g.prepare(kf.index, kf.pose, cam)
+    assert len(np.unique(ids, axis=0)) == len(ids) and new.all()
+    nu, q = g.integrate(kf.index, True, kf.pose, cam, ids, 1)
+    s1, w1, c1 = g.download_chunks(ids)
+    assert (w1 > 0).sum() > 1_000_000 and (c1.reshape(-1, 4)[:, 3] > 0).sum() > 100_000
+    # twice the same observation: weights double exactly, sdf stays within rounding of itself
+    g.integrate(kf.index, True, kf.pose, cam, ids, 1)
+    s2, w2, c2 = g.download_chunks(ids)
+    seen = w1 > 0
+    assert np.array_equal(w2[seen], (w1[seen] + w1[seen]).astype(np.float32))
+    assert np.allclose(s2[seen], s1[seen], rtol=0, atol=2e-5)
+    assert np.array_equal(c2.reshape(-1, 4)[:, 3], 2 * c1.reshape(-1, 4)[:, 3])
+    # remove both observations again
+    for _ in range(2):
+        g.integrate(kf.index, True, kf.pose, cam, ids, 0)
+    s0, w0, c0 = g.download_chunks(ids)
+    assert np.all(w0 == 0) and np.all(s0[seen] == 999.0) and not c0.any()

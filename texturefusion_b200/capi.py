@@ -22,7 +22,7 @@ EXPORTS = [
     "tf_upload_frame", "tf_upload_keyframe_rgb", "tf_release_frame", "tf_frame_device_ptrs",
     "tf_prepare", "tf_integrate", "tf_integrate_group", "tf_remove_chunks", "tf_integrate_frame",
     "tf_integrate_batch", "tf_has_chunk", "tf_chunk_count", "tf_list_chunks", "tf_download_chunks",
-    "tf_atlas_alloc_slot", "tf_atlas_update", "tf_atlas_download", "tf_atlas_patch_size", "tf_sync",
+    "tf_atlas_alloc_slot", "tf_atlas_update", "tf_atlas_download", "tf_atlas_patch_size", "tf_patch_texcoords", "tf_sync",
     "tf_get_counters", "tf_stream", "tf_set_profiling", "tf_get_kernel_time", "tf_get_stage_times", "tf_debug_project",
 ]
 
@@ -124,6 +124,7 @@ def load() -> C.CDLL:
     L.tf_atlas_update.argtypes = [vp, C.POINTER(PatchDesc), i64]
     L.tf_atlas_download.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
     L.tf_atlas_patch_size.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.tf_patch_texcoords.argtypes = [vp, C.c_int32, C.POINTER(Pose), C.POINTER(Camera), i64, vp, vp, vp, vp, vp, vp]
     L.tf_sync.argtypes = [vp]
     L.tf_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.tf_stream.argtypes = [vp]
@@ -376,6 +377,19 @@ class Map:
         out = np.empty((hot_end - hot_start) * 3, np.uint8)
         self._check(self.L.tf_atlas_download(self.h, C.c_uint64(hot_start), C.c_uint64(hot_end), _p(out)))
         return out
+
+    def patch_texcoords(self, frame_index, world_to_camera, cam, offsets, vertices, colors):
+        """Patch::CalculateTexCoords for a batch of meshes; returns (texcoord, texcolor, results[n,6])."""
+        off = np.ascontiguousarray(offsets, np.int64)
+        v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+        c = np.ascontiguousarray(colors, np.float32).reshape(-1, 3)
+        n = len(off) - 1
+        tc = np.empty((len(v), 2), np.float32)
+        col = np.empty((len(v), 3), np.float32)
+        res = np.empty((max(n, 1), 6), np.int32)
+        self._check(self.L.tf_patch_texcoords(self.h, frame_index, C.byref(make_pose(world_to_camera)),
+                                              C.byref(make_camera(cam)), n, _p(off), _p(v), _p(c), _p(tc), _p(col), _p(res)))
+        return tc, col, res[:n]
 
     # misc -----------------------------------------------------------------------------------
     def sync(self):

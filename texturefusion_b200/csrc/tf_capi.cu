@@ -945,6 +945,50 @@ int tf_atlas_download(tf_map* m, uint64_t hot_start, uint64_t hot_end, uint8_t* 
   return TF_OK;
 }
 
+// Patch::CalculateTexCoords for a batch of chunk meshes against one key-frame of the store.
+int tf_patch_texcoords(tf_map* m, int32_t frame_index, const tf_pose* world_to_camera, const tf_camera* cam,
+                       int64_t n_patches, const int64_t* vertex_offsets, const float* vertices, const float* colors,
+                       float* texcoord_out, float* texcolor_out, tf_patch_result* results) {
+  if (!m || !world_to_camera || !cam_ok(m, cam) || n_patches < 0 ||
+      (n_patches > 0 && (!vertex_offsets || !vertices || !colors || !texcoord_out || !texcolor_out || !results)))
+    return fail(m, TF_ERR_INVALID, "tf_patch_texcoords: bad argument");
+  if (n_patches == 0) return TF_OK;
+  const int s = find_slot(m, frame_index);
+  if (s < 0 || !m->slots[s].has_rgb) return fail(m, TF_ERR_NOT_FOUND, "tf_patch_texcoords: key-frame rgb not in the frame store");
+  const int64_t nv = vertex_offsets[n_patches];
+  if (nv < 0 || vertex_offsets[0] != 0) return fail(m, TF_ERR_INVALID, "tf_patch_texcoords: bad offsets");
+  long long* d_off = nullptr;
+  float *d_v = nullptr, *d_c = nullptr, *d_tc = nullptr, *d_col = nullptr;
+  PatchTexResult* d_res = nullptr;
+  int rc = TF_OK;
+  auto ok = [&](cudaError_t e) {
+    if (e != cudaSuccess && rc == TF_OK) rc = fail(m, TF_ERR_CUDA, cudaGetErrorString(e));
+    return e == cudaSuccess;
+  };
+  const size_t nvv = (size_t)std::max<int64_t>(nv, 1);
+  if (ok(dmalloc(&d_off, (size_t)n_patches + 1)) && ok(dmalloc(&d_v, nvv * 3)) && ok(dmalloc(&d_c, nvv * 3)) &&
+      ok(dmalloc(&d_tc, nvv * 2)) && ok(dmalloc(&d_col, nvv * 3)) && ok(dmalloc(&d_res, (size_t)n_patches)) &&
+      ok(cudaMemcpyAsync(d_off, vertex_offsets, (n_patches + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, m->stream)) &&
+      ok(cudaMemcpyAsync(d_v, vertices, nv * 12, cudaMemcpyHostToDevice, m->stream)) &&
+      ok(cudaMemcpyAsync(d_c, colors, nv * 12, cudaMemcpyHostToDevice, m->stream))) {
+    tf_pose_dev T;
+    memcpy(T.m, world_to_camera->m, sizeof(T.m));
+    patch_texcoords_kernel<<<(unsigned)n_patches, kPatchThreads, 0, m->stream>>>(
+        m->slots[s].rgb, m->slots[s].depth, T, (float)(int)cam->fx, (float)(int)cam->fy, (float)(int)cam->cx,
+        (float)(int)cam->cy, m->W, m->H, d_off, d_v, d_c, d_tc, d_col, d_res);
+    ok(cudaGetLastError());
+    m->counters.kernel_launches++;
+    ok(cudaMemcpyAsync(texcoord_out, d_tc, nv * 8, cudaMemcpyDeviceToHost, m->stream));
+    ok(cudaMemcpyAsync(texcolor_out, d_col, nv * 12, cudaMemcpyDeviceToHost, m->stream));
+    ok(cudaMemcpyAsync(results, d_res, n_patches * sizeof(PatchTexResult), cudaMemcpyDeviceToHost, m->stream));
+    ok(cudaStreamSynchronize(m->stream));
+    m->counters.h2d_bytes += nv * 24 + (n_patches + 1) * 8;
+    m->counters.d2h_bytes += nv * 20 + n_patches * (int64_t)sizeof(PatchTexResult);
+  }
+  cudaFree(d_off); cudaFree(d_v); cudaFree(d_c); cudaFree(d_tc); cudaFree(d_col); cudaFree(d_res);
+  return rc;
+}
+
 // ---- counters / profiling ------------------------------------------------------------------------
 
 int tf_get_counters(tf_map* m, tf_counters* out) {

@@ -419,6 +419,18 @@ class Chisel {
     check(tf_upload_frame(map, frame_index, depth, nullptr, quality));
     check(tf_upload_keyframe_rgb(map, frame_index, rgb, colorValid));
   }
+  // Patch::CalculateTexCoords (Structure/Patch.cpp:40-108) for all patches of one key-frame in one
+  // launch.  T_g_l = frame.pose_sophus[0].inverse().matrix().cast<float>() (column-major 16 floats);
+  // mesh p owns vertices [offsets[p], offsets[p+1]).  Fills texcoord (2/vertex), texcolor (3/vertex)
+  // and per patch {boundingbox x, y, w, h, wrong_mapping, flag}.
+  void CalculateTexCoords(int frame_index, const float* T_g_l, const PinholeCamera& camera, int64_t n_patches,
+                          const int64_t* offsets, const float* vertices, const float* colors, float* texcoord,
+                          float* texcolor, tf_patch_result* results) {
+    tf_pose T;
+    std::memcpy(T.m, T_g_l, sizeof(T.m));
+    const tf_camera cam = camera.c_camera();
+    check(tf_patch_texcoords(map, frame_index, &T, &cam, n_patches, offsets, vertices, colors, texcoord, texcolor, results));
+  }
   // Structure/Chisel.cpp:191-196
   void UpdateAtlas(ChunkIDList& chunksToUpdate) { atlas.UpdateBuffers(chunksToUpdate); }
 
