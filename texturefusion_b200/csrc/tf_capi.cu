@@ -109,6 +109,7 @@ struct tf_map {
   // host mirrors
   int64_t n_live = 0;
   int pool_next = 0;
+  int parity = 0;  // which set of bounding-box accumulators the current frame uses
   tf_counters counters{};
 
   // profiling of the integrate kernel
@@ -282,11 +283,12 @@ int launch_cull(tf_map* m, const CullParams& cp, const GroupParams& gp, const fl
   EventPair ep;
   const bool st = m->prof >= 2;
   if (st) prof_begin(m, ep);
-  bbox_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->partial, m->cand_cap);
+  m->parity ^= 1;
+  bbox_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->parity);
   if (st) { prof_end(m, ep, 0); prof_begin(m, ep); }
   if (int rc = check_kernel(m, "bbox_kernel")) return rc;
   launch_pdl(cull_kernel, m->grid_cull, 0, m->stream, cp, depth, m->fs, m->child_mask, m->hit_count, m->local_off,
-             m->word_base, m->hit_cands, m->cfg.n_ranks, m->cfg.rank, m->list_cap);
+             m->word_base, m->hit_cands, m->cfg.n_ranks, m->cfg.rank, m->list_cap, m->parity, m->cand_cap);
   if (st) prof_end(m, ep, 1);
   if (int rc = check_kernel(m, "cull_kernel")) return rc;
   if (do_alloc >= 0) {
@@ -407,8 +409,20 @@ void tf_destroy(tf_map* m) {
 static int reset_device_state(tf_map* m) {
   CUDA_OK(m, cudaMemsetAsync(m->md.keys, 0xFF, (size_t)m->hash_cap * sizeof(unsigned long long), m->stream));
   CUDA_OK(m, cudaMemsetAsync(m->md.slot_flags, 0, (size_t)m->md.max_chunks, m->stream));
-  CUDA_OK(m, cudaMemsetAsync(m->fs, 0, sizeof(FrameState), m->stream));
+  FrameState init;
+  memset(&init, 0, sizeof(init));
+  for (int p = 0; p < 2; p++)
+    for (int k = 0; k < 3; k++) {  // seeds of findCubeCornerByMat: +-1e8 (ordered-int encoding of tf_device.cuh)
+      const float lo = 1e8f, hi = -1e8f;
+      int il, ih;
+      memcpy(&il, &lo, 4);
+      memcpy(&ih, &hi, 4);
+      init.bbox_enc[p][k] = il >= 0 ? il : il ^ 0x7FFFFFFF;
+      init.bbox_enc[p][3 + k] = ih >= 0 ? ih : ih ^ 0x7FFFFFFF;
+    }
+  CUDA_OK(m, cudaMemcpyAsync(m->fs, &init, sizeof(FrameState), cudaMemcpyHostToDevice, m->stream));
   CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  m->parity = 0;
   m->n_live = 0;
   m->pool_next = 0;
   return TF_OK;
