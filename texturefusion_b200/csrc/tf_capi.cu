@@ -58,18 +58,10 @@ struct tf_map {
 
   // per-frame scratch
   int cand_cap = 0, list_cap = 0;
-  unsigned long long* child_mask = nullptr;  // per coarse candidate: which of its children are hit
-  int* local_off = nullptr;                  // exclusive hit count inside the candidate's 32-candidate word
-  int* hit_cands = nullptr;
-  unsigned char* hit_count = nullptr;  // fine hits per coarse candidate (<= 64)
-  int* word_base = nullptr;
+  CullBuffers cb{};  // culling scratch + the frame's chunk list (device arrays, see tf_kernels.cuh)
   float* partial = nullptr;
-  int3* list_ids = nullptr;
-  int* list_slots = nullptr;
-  unsigned char* list_new = nullptr;
   unsigned* list_upd = nullptr;
   float* list_q = nullptr;
-  float* list_setup = nullptr;  // [list_cap][setup_frames][8]: per-(chunk, frame) constants
   int setup_frames = 0;
 
   // mapped pinned result + output staging
@@ -269,16 +261,17 @@ double algorithmic_bytes(const tf_map* m, int64_t n_chunks, const bool* color, i
 int ensure_setup(tf_map* m, int n_frames) {
   if (n_frames <= m->setup_frames) return TF_OK;
   cudaStreamSynchronize(m->stream);
-  cudaFree(m->list_setup);
-  m->list_setup = nullptr;
+  cudaFree(m->cb.list_setup);
+  m->cb.list_setup = nullptr;
   m->setup_frames = 0;
-  CUDA_OK(m, dmalloc(&m->list_setup, (size_t)m->list_cap * n_frames * kSetupStride));
+  CUDA_OK(m, dmalloc(&m->cb.list_setup, (size_t)m->list_cap * n_frames * kSetupStride));
   m->setup_frames = n_frames;
   return TF_OK;
 }
 
-// gp: the frames that will be integrated over the list (n_frames == 0: prepare only)
-int launch_cull(tf_map* m, const CullParams& cp, const GroupParams& gp, const float* depth, int do_alloc) {
+// bbox + culling.  fused: the culling kernel also resolves / creates the chunks and builds the
+// frame's list for the frames of `gp` (else: hit queue only, for alloc_kernel).
+int launch_cull(tf_map* m, const CullParams& cp, const GroupParams& gp, const float* depth, bool fused, bool want_order) {
   if (int rc = ensure_setup(m, std::max(1, gp.n_frames))) return rc;
   EventPair ep;
   const bool st = m->prof >= 2;
@@ -287,19 +280,14 @@ int launch_cull(tf_map* m, const CullParams& cp, const GroupParams& gp, const fl
   bbox_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->parity);
   if (st) { prof_end(m, ep, 0); prof_begin(m, ep); }
   if (int rc = check_kernel(m, "bbox_kernel")) return rc;
-  launch_pdl(cull_kernel, m->grid_cull, 0, m->stream, cp, depth, m->fs, m->child_mask, m->hit_count, m->local_off,
-             m->word_base, m->hit_cands, m->cfg.n_ranks, m->cfg.rank, m->list_cap, m->parity, m->cand_cap);
+  if (fused)
+    launch_pdl(cull_kernel<true>, m->grid_cull, 0, m->stream, cp, gp, m->md, depth, m->fs, m->cb, m->cfg.n_ranks,
+               m->cfg.rank, m->parity, want_order ? 1 : 0);
+  else
+    launch_pdl(cull_kernel<false>, m->grid_cull, 0, m->stream, cp, gp, m->md, depth, m->fs, m->cb, m->cfg.n_ranks,
+               m->cfg.rank, m->parity, 1);
   if (st) prof_end(m, ep, 1);
-  if (int rc = check_kernel(m, "cull_kernel")) return rc;
-  if (do_alloc >= 0) {
-    if (st) prof_begin(m, ep);
-    launch_pdl(alloc_kernel, m->grid_cull, 0, m->stream, cp, gp, m->md, m->fs, (const unsigned long long*)m->child_mask,
-               (const int*)m->local_off, (const int*)m->word_base, (const int*)m->hit_cands, m->list_ids, m->list_slots,
-               m->list_new, m->list_setup, do_alloc);
-    if (st) prof_end(m, ep, 3);
-    if (int rc = check_kernel(m, "alloc_kernel")) return rc;
-  }
-  return TF_OK;
+  return check_kernel(m, "cull_kernel");
 }
 
 int launch_integrate(tf_map* m, const GroupParams& gp, const int* n_dev, int n_host, double bytes,
@@ -312,10 +300,12 @@ int launch_integrate(tf_map* m, const GroupParams& gp, const int* n_dev, int n_h
   for (int f = 0; f < gp.n_frames; f++) any_color |= gp.f[f].rgba != nullptr;
   if (any_color)
     launch_pdl(integrate_kernel<true>, m->grid_integrate_c, integrate_smem_bytes(gp.n_frames), m->stream, gp, m->md,
-               (const int*)m->list_slots, (const float*)m->list_setup, n_dev, n_host, m->list_upd, m->list_q, ff);
+               (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, n_dev, n_host, &m->fs->work_next, m->list_upd,
+               m->list_q, ff);
   else
     launch_pdl(integrate_kernel<false>, m->grid_integrate, integrate_smem_bytes(gp.n_frames), m->stream, gp, m->md,
-               (const int*)m->list_slots, (const float*)m->list_setup, n_dev, n_host, m->list_upd, m->list_q, ff);
+               (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, n_dev, n_host, &m->fs->work_next, m->list_upd,
+               m->list_q, ff);
   if (m->prof) {
     prof_end(m, ep);
     m->ev_pending.back().bytes = bytes;
@@ -344,7 +334,7 @@ int build_group(tf_map* m, const tf_group_frame* frames, int n_frames, const tf_
 
 int upload_ids(tf_map* m, const tf_chunk_id* ids, int64_t n) {
   if (n > m->list_cap) return fail(m, TF_ERR_CAPACITY, "chunk list exceeds the list capacity");
-  CUDA_OK(m, cudaMemcpyAsync(m->list_ids, ids, (size_t)n * sizeof(int3), cudaMemcpyHostToDevice, m->stream));
+  CUDA_OK(m, cudaMemcpyAsync(m->cb.list_ids, ids, (size_t)n * sizeof(int3), cudaMemcpyHostToDevice, m->stream));
   m->counters.h2d_bytes += n * (int64_t)sizeof(int3);
   return TF_OK;
 }
@@ -355,8 +345,8 @@ int lookup_ids(tf_map* m, const tf_chunk_id* ids, int64_t n, bool must_exist, co
   if (int rc = ensure_setup(m, gp ? gp->n_frames : 1)) return rc;
   if (int rc = upload_ids(m, ids, n)) return rc;
   const int grid = (int)std::min<int64_t>(m->grid, (n + kThreads - 1) / kThreads);
-  lookup_kernel<<<std::max(grid, 1), kThreads, 0, m->stream>>>(gp ? *gp : kNoFrames, m->md, m->fs, m->list_ids, (int)n,
-                                                               m->list_slots, m->list_setup);
+  lookup_kernel<<<std::max(grid, 1), kThreads, 0, m->stream>>>(gp ? *gp : kNoFrames, m->md, m->fs, m->cb.list_ids, (int)n,
+                                                               m->cb.list_slots, m->cb.list_hpos, m->cb.list_setup);
   if (int rc = check_kernel(m, "lookup_kernel")) return rc;
   publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);
   if (int rc = check_kernel(m, "publish_kernel")) return rc;
@@ -389,11 +379,12 @@ void tf_destroy(tf_map* m) {
   if (!m) return;
   cudaSetDevice(m->cfg.device);
   if (m->stream) cudaStreamSynchronize(m->stream);
-  cudaFree(m->md.keys); cudaFree(m->md.vals); cudaFree(m->md.pool); cudaFree(m->md.slot_id);
+  cudaFree(m->md.table); cudaFree(m->md.pool); cudaFree(m->md.slot_id);
   cudaFree(m->md.slot_flags); cudaFree(m->md.free_stack); cudaFree(m->fs);
-  cudaFree(m->child_mask); cudaFree(m->local_off); cudaFree(m->hit_cands); cudaFree(m->hit_count); cudaFree(m->word_base);
-  cudaFree(m->partial); cudaFree(m->list_ids); cudaFree(m->list_slots); cudaFree(m->list_new);
-  cudaFree(m->list_upd); cudaFree(m->list_q); cudaFree(m->list_setup); cudaFree(m->dl_sdf); cudaFree(m->dl_w); cudaFree(m->dl_col);
+  cudaFree(m->cb.mask32); cudaFree(m->cb.local_off); cudaFree(m->cb.hit_items); cudaFree(m->cb.hit_count);
+  cudaFree(m->cb.word_base); cudaFree(m->cb.list_cb); cudaFree(m->cb.list_hpos);
+  cudaFree(m->partial); cudaFree(m->cb.list_ids); cudaFree(m->cb.list_slots); cudaFree(m->cb.list_new);
+  cudaFree(m->list_upd); cudaFree(m->list_q); cudaFree(m->cb.list_setup); cudaFree(m->dl_sdf); cudaFree(m->dl_w); cudaFree(m->dl_col);
   cudaFree(m->count_d); cudaFree(m->atlas); cudaFree(m->patch_d);
   cudaFreeHost(m->res_h); cudaFreeHost(m->out_ids_h); cudaFreeHost(m->out_new_h); cudaFreeHost(m->out_upd_h);
   cudaFreeHost(m->out_q_h); cudaFreeHost(m->upd_stage_h); cudaFreeHost(m->q_stage_h);
@@ -407,7 +398,7 @@ void tf_destroy(tf_map* m) {
 }
 
 static int reset_device_state(tf_map* m) {
-  CUDA_OK(m, cudaMemsetAsync(m->md.keys, 0xFF, (size_t)m->hash_cap * sizeof(unsigned long long), m->stream));
+  CUDA_OK(m, cudaMemsetAsync(m->md.table, 0xFF, (size_t)m->hash_cap * sizeof(HashEntry), m->stream));
   CUDA_OK(m, cudaMemsetAsync(m->md.slot_flags, 0, (size_t)m->md.max_chunks, m->stream));
   FrameState init;
   memset(&init, 0, sizeof(init));
@@ -499,8 +490,7 @@ int tf_create(tf_map** out, const tf_config* cfg) {
   m->md.hash_mask = (unsigned)hc - 1;
   m->md.n_ranks = cfg->n_ranks;
   m->md.rank = cfg->rank;
-  C_OK(dmalloc(&m->md.keys, (size_t)hc));
-  C_OK(dmalloc(&m->md.vals, (size_t)hc));
+  C_OK(dmalloc(&m->md.table, (size_t)hc));
   C_OK(cudaMalloc((void**)&m->md.pool, (size_t)max_chunks * kChunkBytes));
   C_OK(dmalloc(&m->md.slot_id, (size_t)max_chunks));
   C_OK(dmalloc(&m->md.slot_flags, (size_t)max_chunks));
@@ -509,15 +499,19 @@ int tf_create(tf_map** out, const tf_config* cfg) {
 
   m->cand_cap = 1 << 22;  // coarse candidates per frame (4^3-chunk blocks at <= 10 mm voxels)
   m->list_cap = 1 << 19;
-  C_OK(dmalloc(&m->child_mask, (size_t)m->cand_cap));
-  C_OK(dmalloc(&m->local_off, (size_t)m->cand_cap));
-  C_OK(dmalloc(&m->hit_cands, (size_t)m->cand_cap));
-  C_OK(dmalloc(&m->hit_count, (size_t)m->cand_cap + 32));
-  C_OK(dmalloc(&m->word_base, (size_t)m->cand_cap / 32));
+  C_OK(dmalloc(&m->cb.mask32, (size_t)m->cand_cap * 2));
+  C_OK(dmalloc(&m->cb.local_off, (size_t)m->cand_cap));
+  C_OK(dmalloc(&m->cb.hit_items, (size_t)m->cand_cap * 2));
+  C_OK(dmalloc(&m->cb.hit_count, (size_t)m->cand_cap * 2 + 64));
+  C_OK(dmalloc(&m->cb.word_base, (size_t)m->cand_cap / 32));
+  C_OK(dmalloc(&m->cb.list_cb, (size_t)m->list_cap));
+  C_OK(dmalloc(&m->cb.list_hpos, (size_t)m->list_cap));
+  m->cb.list_cap = m->list_cap;
+  m->cb.cand_cap = m->cand_cap;
   C_OK(dmalloc(&m->partial, (size_t)m->grid * 6));
-  C_OK(dmalloc(&m->list_ids, (size_t)m->list_cap));
-  C_OK(dmalloc(&m->list_slots, (size_t)m->list_cap));
-  C_OK(dmalloc(&m->list_new, (size_t)m->list_cap));
+  C_OK(dmalloc(&m->cb.list_ids, (size_t)m->list_cap));
+  C_OK(dmalloc(&m->cb.list_slots, (size_t)m->list_cap));
+  C_OK(dmalloc(&m->cb.list_new, (size_t)m->list_cap));
   C_OK(dmalloc(&m->list_upd, (size_t)m->list_cap));
   C_OK(dmalloc(&m->list_q, (size_t)m->list_cap));
   C_OK(dmalloc(&m->count_d, 1));
@@ -646,7 +640,7 @@ int tf_prepare(tf_map* m, int32_t frame_index, const tf_pose* pose, const tf_cam
   make_cull_params(m->cfg.voxel_res, m->cfg.trunc, *pose, *cam, cp);
   // pass 1: culling only, to learn the list length before anything is created
   static const GroupParams kNoFrames{};
-  if (int rc = launch_cull(m, cp, kNoFrames, m->slots[s].depth, -1)) return rc;
+  if (int rc = launch_cull(m, cp, kNoFrames, m->slots[s].depth, false, true)) return rc;
   publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);
   if (int rc = check_kernel(m, "publish_kernel")) return rc;
   CUDA_OK(m, cudaStreamSynchronize(m->stream));
@@ -656,14 +650,13 @@ int tf_prepare(tf_map* m, int32_t frame_index, const tf_pose* pose, const tf_cam
   if (n > cap || (n > 0 && (!ids_out || !is_new_out)))
     return fail(m, TF_ERR_CAPACITY, "tf_prepare: output capacity too small");
   // pass 2: HasChunk / CreateChunk
-  alloc_kernel<<<m->grid_cull, kThreads, 0, m->stream>>>(cp, kNoFrames, m->md, m->fs, m->child_mask, m->local_off, m->word_base,
-                                                    m->hit_cands, m->list_ids, m->list_slots, m->list_new, m->list_setup, 1);
+  alloc_kernel<<<m->grid_cull, kThreads, 0, m->stream>>>(cp, kNoFrames, m->md, m->fs, m->cb);
   if (int rc = check_kernel(m, "alloc_kernel")) return rc;
   publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);
   if (int rc = check_kernel(m, "publish_kernel")) return rc;
   if (n > 0) {
-    CUDA_OK(m, cudaMemcpyAsync(ids_out, m->list_ids, (size_t)n * sizeof(int3), cudaMemcpyDeviceToHost, m->stream));
-    CUDA_OK(m, cudaMemcpyAsync(is_new_out, m->list_new, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(m, cudaMemcpyAsync(ids_out, m->cb.list_ids, (size_t)n * sizeof(int3), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(m, cudaMemcpyAsync(is_new_out, m->cb.list_new, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
     m->counters.d2h_bytes += n * 13;
   }
   CUDA_OK(m, cudaStreamSynchronize(m->stream));
@@ -711,7 +704,7 @@ int tf_remove_chunks(tf_map* m, const tf_chunk_id* ids, int64_t n) {
   if (n == 0) return TF_OK;
   if (int rc = upload_ids(m, ids, n)) return rc;
   const int grid = (int)std::min<int64_t>(m->grid, (n + kThreads - 1) / kThreads);
-  remove_kernel<<<std::max(grid, 1), kThreads, 0, m->stream>>>(m->md, m->fs, m->list_ids, (int)n);
+  remove_kernel<<<std::max(grid, 1), kThreads, 0, m->stream>>>(m->md, m->fs, m->cb.list_ids, (int)n);
   if (int rc = check_kernel(m, "remove_kernel")) return rc;
   publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);
   if (int rc = check_kernel(m, "publish_kernel")) return rc;
@@ -730,13 +723,14 @@ static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, co
   const int s = find_slot(m, frames[0].frame_index);
   CullParams cp;
   make_cull_params(m->cfg.voxel_res, m->cfg.trunc, frames[0].pose, *cam, cp);
-  if (int rc = launch_cull(m, cp, gp, m->slots[s].depth, 1)) return rc;
+  const bool want_lists = ids_out || new_out || upd_out || q_out;
+  if (int rc = launch_cull(m, cp, gp, m->slots[s].depth, true, want_lists)) return rc;
   const int ocap = (int)std::min<int64_t>(cap, m->list_cap);
   FusedFinalize ff{};
   ff.enabled = 1;
+  ff.ordered = want_lists ? 1 : 0;
   ff.fs = m->fs;
-  ff.list_ids = m->list_ids;
-  ff.list_new = m->list_new;
+  ff.cb = m->cb;
   ff.ids_out = ids_out ? m->out_ids_d : nullptr;
   ff.new_out = new_out ? m->out_new_d : nullptr;
   ff.upd_out = upd_out ? m->out_upd_d : nullptr;
@@ -820,13 +814,34 @@ int tf_integrate_batch(tf_map* m, const tf_batch_item* items, int64_t n_items, c
   return TF_OK;
 }
 
+#ifdef TF_TIMELINE
+// Debug build only: per-kernel device timestamps of the last frame (see TL_MARK).
+extern "C" int tf_debug_timeline(tf_map* m, unsigned long long* out32, int reset) {
+  if (!m) return TF_ERR_INVALID;
+  cudaStreamSynchronize(m->stream);
+  if (out32) {
+    cudaMemcpyFromSymbol(out32, g_timeline, sizeof(unsigned long long) * 32);
+    FrameState f;
+    cudaMemcpy(&f, m->fs, sizeof(f), cudaMemcpyDeviceToHost);
+    out32[29] = f.n_coarse;
+    out32[30] = f.n_hit_cands;
+    out32[31] = f.n_list;
+  }
+  if (reset) {
+    unsigned long long z[32] = {};
+    cudaMemcpyToSymbol(g_timeline, z, sizeof(z));
+  }
+  return TF_OK;
+}
+#endif
+
 // ---- queries ---------------------------------------------------------------------------------
 
 int tf_has_chunk(tf_map* m, tf_chunk_id id) {
   if (!m) return TF_ERR_INVALID;
   if (int rc = lookup_ids(m, &id, 1, false)) return rc;
   int slot = -1;
-  CUDA_OK(m, cudaMemcpy(&slot, m->list_slots, sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_OK(m, cudaMemcpy(&slot, m->cb.list_slots, sizeof(int), cudaMemcpyDeviceToHost));
   return slot >= 0 ? 1 : 0;  // (a lazy bit may be set; the sign is what matters)
 }
 
@@ -864,7 +879,7 @@ int tf_download_chunks(tf_map* m, const tf_chunk_id* ids, int64_t n, float* sdf,
     const int64_t cnt = std::min<int64_t>(m->dl_cap, n - base);
     if (int rc = lookup_ids(m, ids + base, cnt, true)) return rc;
     const int grid = (int)std::min<int64_t>(m->grid * 4, (cnt + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    download_kernel<<<std::max(grid, 1), kThreads, 0, m->stream>>>(m->md, m->list_slots, (int)cnt, sdf ? m->dl_sdf : nullptr,
+    download_kernel<<<std::max(grid, 1), kThreads, 0, m->stream>>>(m->md, m->cb.list_slots, (int)cnt, sdf ? m->dl_sdf : nullptr,
                                                                    weight ? m->dl_w : nullptr, color ? m->dl_col : nullptr);
     if (int rc = check_kernel(m, "download_kernel")) return rc;
     if (sdf) CUDA_OK(m, cudaMemcpyAsync(sdf + base * 512, m->dl_sdf, (size_t)cnt * 2048, cudaMemcpyDeviceToHost, m->stream));
