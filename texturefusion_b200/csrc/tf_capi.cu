@@ -738,7 +738,7 @@ static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, co
   ff.out_cap = ocap;
   ff.res = m->res_d;
   // integrate + Finalize (flags, garbage collection, result publication) in one kernel
-  if (int rc = launch_integrate(m, gp, &m->fs->n_list, 0, -1, &ff)) return rc;
+  if (int rc = launch_integrate(m, gp, &m->fs->n_work, 0, -1, &ff)) return rc;
   CUDA_OK(m, cudaStreamSynchronize(m->stream));
   absorb_result(m);
   const FrameResultHost r = *m->res_h;
@@ -816,6 +816,12 @@ int tf_integrate_batch(tf_map* m, const tf_batch_item* items, int64_t n_items, c
 
 #ifdef TF_TIMELINE
 // Debug build only: per-kernel device timestamps of the last frame (see TL_MARK).
+extern "C" int tf_debug_trace(tf_map* m, unsigned long long* out512) {
+  if (!m || !out512) return TF_ERR_INVALID;
+  cudaStreamSynchronize(m->stream);
+  cudaMemcpyFromSymbol(out512, g_trace, sizeof(unsigned long long) * 512);
+  return TF_OK;
+}
 extern "C" int tf_debug_timeline(tf_map* m, unsigned long long* out32, int reset) {
   if (!m) return TF_ERR_INVALID;
   cudaStreamSynchronize(m->stream);
@@ -830,6 +836,8 @@ extern "C" int tf_debug_timeline(tf_map* m, unsigned long long* out32, int reset
   if (reset) {
     unsigned long long z[32] = {};
     cudaMemcpyToSymbol(g_timeline, z, sizeof(z));
+    static unsigned long long zt[512] = {};
+    cudaMemcpyToSymbol(g_trace, zt, sizeof(zt));
   }
   return TF_OK;
 }

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--flush-read", action="store_true", help="after the write flush, read a second buffer (clean L2 lines)")
     args = ap.parse_args()
     cam = synth.Camera()
     n = args.steps + args.warmup
@@ -33,11 +34,15 @@ def main():
     L = m.L
     L.tf_debug_timeline.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
     flush = torch.empty(128 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    flush2 = torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device="cuda")
     for fr in seq.frames:
         m.upload_frame(fr.index, fr.depth, fr.rgba() if fr.is_keyframe else None, fr.quality if fr.is_keyframe else None)
     camc = capi.make_camera(cam)
     st = capi.FrameStats()
     out = (C.c_uint64 * 32)()
+    L.tf_debug_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    trace = (C.c_uint64 * 512)()
+    traces = []
     rows = []
     cnt = []
     walls = []
@@ -45,6 +50,8 @@ def main():
         pose = capi.make_pose(fr.pose)
         if not args.no_flush:
             flush.fill_(1.0)
+            if args.flush_read:
+                sink = flush2.sum()
         torch.cuda.synchronize()
         L.tf_debug_timeline(m.h, None, 1)
         t0 = time.perf_counter()
@@ -55,6 +62,10 @@ def main():
         L.tf_debug_timeline(m.h, out, 0)
         if i < args.warmup:
             continue
+        L.tf_debug_trace(m.h, trace)
+        tr = np.array(trace[:], dtype=np.float64).reshape(16, 32)
+        tr[tr == 0] = np.nan
+        traces.append((tr - float((~int(out[0])) & 0xFFFFFFFFFFFFFFFF)) / 1e3)
         a = np.array(out[:24], dtype=np.uint64).reshape(6, 4)
         cnt.append([int(out[28]), int(out[29]), int(out[30]), int(out[31])])
         t = np.empty((6, 4))
@@ -77,6 +88,14 @@ def main():
     print(f"integrate internals (latest block, warp 0): list length known {r[5,0]:.2f}, first chunk arrived {r[5,1]:.2f}, first chunk done {r[5,2]:.2f}")
     c = np.mean(np.array(cnt, dtype=np.float64), axis=0)
     print(f"mean per frame: coarse hits {c[0]:.0f}, coarse candidates {c[1]:.0f}, hit candidates {c[2]:.0f}, list {c[3]:.0f}")
+    tr = np.nanmean(np.stack(traces), axis=0)
+    names_t = ["kernel n known", "loop top", "bulk issued", "p0 projected", "p0 gathered", "p0 chunk arrived", "p0 updated",
+               "p1 projected", "p1 gathered", "p1 (arrived)", "p1 updated", "frames done", "written back"]
+    print("per-warp trace (warp 0 of blocks 0,37,...; us after bbox start; mean over frames); chunk 0 | chunk 1")
+    for k, nm in enumerate(names_t):
+        a = " ".join(f"{tr[b, k]:6.1f}" for b in range(0, 16, 3))
+        bb = " ".join(f"{tr[b, 16 + k]:6.1f}" for b in range(0, 16, 3))
+        print(f"  {nm:18s} {a}  | {bb}")
     print(f"host call wall: mean {np.mean(walls):.1f} us, median {np.median(walls):.1f} us")
     m.close()
 
