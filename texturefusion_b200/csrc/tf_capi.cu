@@ -5,9 +5,13 @@
 // quality / rgb planes kept in HBM), per-frame scratch lists and the texture atlas.
 // Every stage of a frame runs as a chain of kernels on one stream with device-side work
 // counts; the host synchronises once per call, when it needs the results.
+#ifdef TF_TIMELINE
+#include <chrono>
+#endif
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,6 +48,17 @@ struct EventPair {
 constexpr int kStages = 6;
 
 }  // namespace
+
+// The fused per-frame chain (bbox -> cull+alloc -> integrate+finalize) as an instantiated CUDA
+// graph: one graph launch instead of three kernel launches; the kernel arguments of the frame are
+// patched in with cudaGraphExecKernelNodeSetParams.
+struct FrameGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t node[3] = {nullptr, nullptr, nullptr};  // bbox, cull, integrate
+  cudaKernelNodeParams kp[3] = {};
+  bool failed = false;  // capture / instantiation not possible: use plain launches
+};
 
 struct tf_map {
   tf_config cfg;
@@ -104,6 +119,10 @@ struct tf_map {
   int parity = 0;  // which set of bounding-box accumulators the current frame uses
   tf_counters counters{};
 
+  // CUDA graphs of the fused per-frame chain, one per (colour, group size); see fused_group
+  FrameGraph graphs[2][kMaxGroupFrames + 1];
+  unsigned seq = 0;  // completion stamp of the last fused frame (FrameResultHost::seq)
+
   // profiling of the integrate kernel
   int prof = 0;  // 1: integrate kernel only, 2: every stage of the fused pipeline
   std::vector<EventPair> ev_pool, ev_pending;
@@ -132,6 +151,13 @@ template <class T>
 cudaError_t dmalloc(T** p, size_t n) {
   return cudaMalloc((void**)p, n * sizeof(T));
 }
+
+#ifdef TF_TIMELINE
+static double g_host_t[16];
+#define HT(k) (g_host_t[k] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count())
+#else
+#define HT(k) ((void)0)
+#endif
 
 // Launch with programmatic stream serialization: the kernel may start while its predecessor on
 // the stream is still running and synchronises with it through griddepcontrol.wait.
@@ -277,7 +303,9 @@ int launch_cull(tf_map* m, const CullParams& cp, const GroupParams& gp, const fl
   const bool st = m->prof >= 2;
   if (st) prof_begin(m, ep);
   m->parity ^= 1;
+  HT(2);
   bbox_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->parity);
+  HT(3);
   if (st) { prof_end(m, ep, 0); prof_begin(m, ep); }
   if (int rc = check_kernel(m, "bbox_kernel")) return rc;
   if (fused)
@@ -287,6 +315,7 @@ int launch_cull(tf_map* m, const CullParams& cp, const GroupParams& gp, const fl
     launch_pdl(cull_kernel<false>, m->grid_cull, 0, m->stream, cp, gp, m->md, depth, m->fs, m->cb, m->cfg.n_ranks,
                m->cfg.rank, m->parity, 1);
   if (st) prof_end(m, ep, 1);
+  HT(4);
   return check_kernel(m, "cull_kernel");
 }
 
@@ -375,10 +404,20 @@ void tf_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
+static void destroy_graphs(tf_map* m) {
+  for (auto& row : m->graphs)
+    for (auto& fg : row) {
+      if (fg.exec) cudaGraphExecDestroy(fg.exec);
+      if (fg.graph) cudaGraphDestroy(fg.graph);
+      fg = FrameGraph{};
+    }
+}
+
 void tf_destroy(tf_map* m) {
   if (!m) return;
   cudaSetDevice(m->cfg.device);
   if (m->stream) cudaStreamSynchronize(m->stream);
+  destroy_graphs(m);
   cudaFree(m->md.table); cudaFree(m->md.pool); cudaFree(m->md.slot_id);
   cudaFree(m->md.slot_flags); cudaFree(m->md.free_stack); cudaFree(m->fs);
   cudaFree(m->cb.mask32); cudaFree(m->cb.local_off); cudaFree(m->cb.hit_items); cudaFree(m->cb.hit_count);
@@ -713,20 +752,131 @@ int tf_remove_chunks(tf_map* m, const tf_chunk_id* ids, int64_t n) {
   return TF_OK;
 }
 
-// Shared tail of the fused pipelines: prepare on frames[0], integrate the group, finalize.
+// ---- the fused per-frame chain ---------------------------------------------------------------------
+
+// Arguments of the three kernels of one fused frame (kept alive until the launch call returns).
+struct FrameArgs {
+  CullParams cp;
+  GroupParams gp;
+  const float* depth;
+  int parity, want_order;
+  bool any_color;
+  FusedFinalize ff;
+  const int* n_dev;
+  int n_host;
+};
+
+static void launch_frame_kernels(tf_map* m, FrameArgs& a) {
+  bbox_kernel<<<m->grid, kThreads, 0, m->stream>>>(a.cp, a.depth, m->fs, a.parity);
+  launch_pdl(cull_kernel<true>, m->grid_cull, 0, m->stream, a.cp, a.gp, m->md, a.depth, m->fs, m->cb, m->cfg.n_ranks,
+             m->cfg.rank, a.parity, a.want_order);
+  if (a.any_color)
+    launch_pdl(integrate_kernel<true>, m->grid_integrate_c, integrate_smem_bytes(a.gp.n_frames), m->stream, a.gp, m->md,
+               (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, a.n_dev,
+               a.n_host, &m->fs->work_next, m->list_upd, m->list_q, a.ff);
+  else
+    launch_pdl(integrate_kernel<false>, m->grid_integrate, integrate_smem_bytes(a.gp.n_frames), m->stream, a.gp, m->md,
+               (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, a.n_dev,
+               a.n_host, &m->fs->work_next, m->list_upd, m->list_q, a.ff);
+}
+
+static bool graphs_enabled() {  // on by default; TEXFUSION_B200_GRAPH=0 uses plain launches
+  static const bool on = [] { const char* e = getenv("TEXFUSION_B200_GRAPH"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+// Captures the chain once per (colour, group size).  Returns false when graphs cannot be used.
+static bool build_frame_graph(tf_map* m, FrameGraph& fg, FrameArgs& a) {
+  if (fg.failed) return false;
+  fg.failed = true;  // until everything below has worked
+  if (cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+  launch_frame_kernels(m, a);
+  cudaGraph_t g = nullptr;
+  if (cudaStreamEndCapture(m->stream, &g) != cudaSuccess || !g) { cudaGetLastError(); return false; }
+  fg.graph = g;
+  if (cudaGraphInstantiate(&fg.exec, g, 0) != cudaSuccess) { cudaGetLastError(); return false; }
+  cudaGraphNode_t nodes[8];
+  size_t nn = 8;
+  if (cudaGraphGetNodes(g, nodes, &nn) != cudaSuccess || nn != 3) { cudaGetLastError(); return false; }
+  const void* fn[3] = {(const void*)bbox_kernel, (const void*)cull_kernel<true>,
+                       a.any_color ? (const void*)integrate_kernel<true> : (const void*)integrate_kernel<false>};
+  for (size_t i = 0; i < nn; i++) {
+    cudaKernelNodeParams kp{};
+    if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) { cudaGetLastError(); return false; }
+    for (int k = 0; k < 3; k++)
+      if (kp.func == fn[k]) { fg.node[k] = nodes[i]; fg.kp[k] = kp; }
+  }
+  if (!fg.node[0] || !fg.node[1] || !fg.node[2]) return false;
+  fg.failed = false;
+  return true;
+}
+
+static int launch_frame_graph(tf_map* m, FrameGraph& fg, FrameArgs& a) {
+  // argument lists in declaration order of the kernels (tf_kernels.cuh)
+  const int* list_slots = m->cb.list_slots;
+  const int* list_hpos = m->cb.list_hpos;
+  const float* list_setup = m->cb.list_setup;
+  int* work_next = &m->fs->work_next;
+  void* p_bbox[] = {&a.cp, &a.depth, &m->fs, &a.parity};
+  void* p_cull[] = {&a.cp, &a.gp, &m->md, &a.depth, &m->fs, &m->cb, &m->cfg.n_ranks, &m->cfg.rank, &a.parity, &a.want_order};
+  void* p_int[] = {&a.gp, &m->md, &list_slots, &list_hpos, &list_setup, &a.n_dev, &a.n_host, &work_next, &m->list_upd,
+                   &m->list_q, &a.ff};
+  void** params[3] = {p_bbox, p_cull, p_int};
+  HT(2);
+  for (int k = 0; k < 3; k++) {
+    fg.kp[k].kernelParams = params[k];
+    fg.kp[k].extra = nullptr;
+    CUDA_OK(m, cudaGraphExecKernelNodeSetParams(fg.exec, fg.node[k], &fg.kp[k]));
+  }
+  HT(3);
+  CUDA_OK(m, cudaGraphLaunch(fg.exec, m->stream));
+  HT(4);
+  m->counters.kernel_launches += 3;
+  return TF_OK;
+}
+
+// Waits for the completion stamp of a fused frame (written last by publish_frame into mapped host
+// memory).  Polling it returns a few microseconds earlier than cudaStreamSynchronize; the stream
+// is queried now and then so that a failed kernel cannot hang the caller.
+static int wait_frame(tf_map* m, unsigned seq) {
+  volatile unsigned* p = &m->res_h->seq;
+  for (unsigned it = 1; *p != seq; it++) {
+    if ((it & 0x3fffu) == 0) {
+      const cudaError_t e = cudaStreamQuery(m->stream);
+      if (e == cudaSuccess) break;  // finished: the stamp is there (or the kernels did not publish)
+      if (e != cudaErrorNotReady) return fail(m, TF_ERR_CUDA, std::string("fused frame: ") + cudaGetErrorString(e));
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  if (*p != seq) {  // stream idle without a stamp: surface whatever went wrong
+    CUDA_OK(m, cudaStreamSynchronize(m->stream));
+    if (*p != seq) return fail(m, TF_ERR_CUDA, "fused frame: kernels finished without publishing a result");
+  }
+  return TF_OK;
+}
+
+// Shared body of the fused pipelines: prepare on frames[0], integrate the group, finalize.
 static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, const tf_camera* cam,
                        tf_frame_stats* stats, tf_chunk_id* ids_out, uint8_t* new_out, uint8_t* upd_out,
                        float* q_out, int64_t cap) {
-  GroupParams gp;
+  HT(0);
+  FrameArgs a;
   bool color[kMaxGroupFrames];
-  if (int rc = build_group(m, frames, n_frames, cam, gp, color)) return rc;
+  if (int rc = build_group(m, frames, n_frames, cam, a.gp, color)) return rc;
   const int s = find_slot(m, frames[0].frame_index);
-  CullParams cp;
-  make_cull_params(m->cfg.voxel_res, m->cfg.trunc, frames[0].pose, *cam, cp);
+  make_cull_params(m->cfg.voxel_res, m->cfg.trunc, frames[0].pose, *cam, a.cp);
+  if (int rc = ensure_setup(m, n_frames)) return rc;
+  HT(1);
   const bool want_lists = ids_out || new_out || upd_out || q_out;
-  if (int rc = launch_cull(m, cp, gp, m->slots[s].depth, true, want_lists)) return rc;
   const int ocap = (int)std::min<int64_t>(cap, m->list_cap);
-  FusedFinalize ff{};
+  a.depth = m->slots[s].depth;
+  a.want_order = want_lists ? 1 : 0;
+  a.any_color = false;
+  for (int f = 0; f < n_frames; f++) a.any_color |= color[f];
+  a.n_dev = &m->fs->n_work;
+  a.n_host = 0;
+  FusedFinalize& ff = a.ff;
+  ff = FusedFinalize{};
   ff.enabled = 1;
   ff.ordered = want_lists ? 1 : 0;
   ff.fs = m->fs;
@@ -737,9 +887,27 @@ static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, co
   ff.q_out = q_out ? m->out_q_d : nullptr;
   ff.out_cap = ocap;
   ff.res = m->res_d;
-  // integrate + Finalize (flags, garbage collection, result publication) in one kernel
-  if (int rc = launch_integrate(m, gp, &m->fs->n_work, 0, -1, &ff)) return rc;
-  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  ff.seq = ++m->seq;
+
+  // bbox -> cull (+ HasChunk / CreateChunk) -> integrate (+ Finalize, garbage collection, publication)
+  FrameGraph& fg = m->graphs[a.any_color ? 1 : 0][n_frames];
+  bool launched = false;
+  if (m->prof == 0 && graphs_enabled() && (fg.exec || build_frame_graph(m, fg, a)) && !fg.failed) {
+    m->parity ^= 1;
+    a.parity = m->parity;
+    if (int rc = launch_frame_graph(m, fg, a)) return rc;
+    HT(5);
+    if (int rc = wait_frame(m, ff.seq)) return rc;
+    launched = true;
+  }
+  if (!launched) {  // plain launches (profiling with events between the stages, or graphs unavailable)
+    if (int rc = launch_cull(m, a.cp, a.gp, a.depth, true, want_lists)) return rc;
+    a.parity = m->parity;
+    if (int rc = launch_integrate(m, a.gp, a.n_dev, 0, -1, &ff)) return rc;
+    HT(5);
+    CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  }
+  HT(6);
   absorb_result(m);
   const FrameResultHost r = *m->res_h;
   prof_collect(m, algorithmic_bytes(m, r.n_chunks, color, n_frames));
@@ -816,10 +984,12 @@ int tf_integrate_batch(tf_map* m, const tf_batch_item* items, int64_t n_items, c
 
 #ifdef TF_TIMELINE
 // Debug build only: per-kernel device timestamps of the last frame (see TL_MARK).
+extern "C" int tf_debug_host(double* out16) { memcpy(out16, g_host_t, sizeof(g_host_t)); return 0; }
 extern "C" int tf_debug_trace(tf_map* m, unsigned long long* out512) {
   if (!m || !out512) return TF_ERR_INVALID;
   cudaStreamSynchronize(m->stream);
   cudaMemcpyFromSymbol(out512, g_trace, sizeof(unsigned long long) * 512);
+  cudaMemcpyFromSymbol(out512 + 512, g_trace2, sizeof(unsigned long long) * 512);
   return TF_OK;
 }
 extern "C" int tf_debug_timeline(tf_map* m, unsigned long long* out32, int reset) {
@@ -838,6 +1008,7 @@ extern "C" int tf_debug_timeline(tf_map* m, unsigned long long* out32, int reset
     cudaMemcpyToSymbol(g_timeline, z, sizeof(z));
     static unsigned long long zt[512] = {};
     cudaMemcpyToSymbol(g_trace, zt, sizeof(zt));
+    cudaMemcpyToSymbol(g_trace2, zt, sizeof(zt));
   }
   return TF_OK;
 }

@@ -67,6 +67,7 @@ inline void make_cull_params(float res, const tf_truncation& tr, const tf_pose& 
   cp.dtn_c = neg_trunc + diag * step;
   cp.dtn_f = neg_trunc + diag;
   cp.step = step;
+  cp.step_log2 = step == 4 ? 2 : 0;
   cp.trunc = TruncDev{tr.quad, tr.lin, tr.cst, tr.scale, tr.weight};
 }
 

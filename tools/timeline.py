@@ -41,7 +41,10 @@ def main():
     st = capi.FrameStats()
     out = (C.c_uint64 * 32)()
     L.tf_debug_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-    trace = (C.c_uint64 * 512)()
+    trace = (C.c_uint64 * 1024)()
+    host = (C.c_double * 16)()
+    hosts = []
+    traces2 = []
     traces = []
     rows = []
     cnt = []
@@ -62,10 +65,16 @@ def main():
         L.tf_debug_timeline(m.h, out, 0)
         if i < args.warmup:
             continue
+        L.tf_debug_host(host)
+        hosts.append([host[k] - host[0] for k in range(7)] + [(t1 - t0) * 1e6])
         L.tf_debug_trace(m.h, trace)
-        tr = np.array(trace[:], dtype=np.float64).reshape(16, 32)
+        t_zero = float((~int(out[0])) & 0xFFFFFFFFFFFFFFFF)
+        tr = np.array(trace[:512], dtype=np.float64).reshape(16, 32)
         tr[tr == 0] = np.nan
-        traces.append((tr - float((~int(out[0])) & 0xFFFFFFFFFFFFFFFF)) / 1e3)
+        traces.append((tr - t_zero) / 1e3)
+        tr = np.array(trace[512:], dtype=np.float64).reshape(16, 32)
+        tr[tr == 0] = np.nan
+        traces2.append((tr - t_zero) / 1e3)
         a = np.array(out[:24], dtype=np.uint64).reshape(6, 4)
         cnt.append([int(out[28]), int(out[29]), int(out[30]), int(out[31])])
         t = np.empty((6, 4))
@@ -88,6 +97,11 @@ def main():
     print(f"integrate internals (latest block, warp 0): list length known {r[5,0]:.2f}, first chunk arrived {r[5,1]:.2f}, first chunk done {r[5,2]:.2f}")
     c = np.mean(np.array(cnt, dtype=np.float64), axis=0)
     print(f"mean per frame: coarse hits {c[0]:.0f}, coarse candidates {c[1]:.0f}, hit candidates {c[2]:.0f}, list {c[3]:.0f}")
+    tr = np.nanmean(np.stack(traces2), axis=0)
+    print("cull per-warp trace (warp 0 of blocks 0,37,...)")
+    for k, nm in enumerate(["waited", "grid known", "coarse tested", "coarse sync", "fine tested", "chunks resolved",
+                            "list pos known", "task done", "round done"]):
+        print(f"  {nm:18s} " + " ".join(f"{tr[b, k]:6.1f}" for b in range(0, 16)))
     tr = np.nanmean(np.stack(traces), axis=0)
     names_t = ["kernel n known", "loop top", "bulk issued", "p0 projected", "p0 gathered", "p0 chunk arrived", "p0 updated",
                "p1 projected", "p1 gathered", "p1 (arrived)", "p1 updated", "frames done", "written back"]
@@ -96,6 +110,9 @@ def main():
         a = " ".join(f"{tr[b, k]:6.1f}" for b in range(0, 16, 3))
         bb = " ".join(f"{tr[b, 16 + k]:6.1f}" for b in range(0, 16, 3))
         print(f"  {nm:18s} {a}  | {bb}")
+    hm = np.median(np.array(hosts), axis=0)
+    print("host (us after entry, median): params ready %.1f | bbox launch %.1f..%.1f | cull launched %.1f | integrate launched %.1f | sync returned %.1f | call %.1f"
+          % (hm[1], hm[2], hm[3], hm[4], hm[5], hm[6], hm[7]))
     print(f"host call wall: mean {np.mean(walls):.1f} us, median {np.median(walls):.1f} us")
     m.close()
 
