@@ -38,6 +38,8 @@ struct FrameSlot {
   float* quality = nullptr;
   unsigned char* rgb = nullptr;
   unsigned char* valid = nullptr;
+  cudaEvent_t ready = nullptr;  // recorded on the copy stream after the slot's uploads
+  bool pending = false;         // uploads in flight: consumers on the compute stream wait for `ready`
 };
 
 struct EventPair {
@@ -55,16 +57,19 @@ constexpr int kStages = 6;
 struct FrameGraph {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
-  cudaGraphNode_t node[3] = {nullptr, nullptr, nullptr};  // bbox, cull, integrate
-  cudaKernelNodeParams kp[3] = {};
+  cudaGraphNode_t node[4] = {nullptr, nullptr, nullptr, nullptr};  // bbox, cull, integrate, export
+  cudaKernelNodeParams kp[4] = {};
   bool failed = false;  // capture / instantiation not possible: use plain launches
 };
 
 struct tf_map {
   tf_config cfg;
   int W = 0, H = 0, npix = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // all kernels and read-backs
+  cudaStream_t copy_stream = nullptr;  // frame uploads: the next frame's H2D copy overlaps the current frame's kernels
   std::string err;
+  float* slab_depth = nullptr;          // frame store: depth planes of all slots
+  unsigned char* slab_color = nullptr;  // rgba | quality | rgb | valid planes of all slots
   int sm_count = 0, grid = 0, grid_cull = 0, grid_integrate = 0, grid_integrate_c = 0;
 
   MapDev md{};
@@ -86,6 +91,10 @@ struct tf_map {
   unsigned char* out_new_h = nullptr;
   unsigned char* out_upd_h = nullptr;
   float* out_q_h = nullptr;
+  int3* st_ids = nullptr;  // device staging of the ordered per-chunk outputs (export_kernel)
+  unsigned char* st_new = nullptr;
+  unsigned char* st_upd = nullptr;
+  float* st_q = nullptr;
   int3* out_ids_d = nullptr;
   unsigned char* out_new_d = nullptr;
   unsigned char* out_upd_d = nullptr;
@@ -120,7 +129,7 @@ struct tf_map {
   tf_counters counters{};
 
   // CUDA graphs of the fused per-frame chain, one per (colour, group size); see fused_group
-  FrameGraph graphs[2][kMaxGroupFrames + 1];
+  FrameGraph graphs[2][2][kMaxGroupFrames + 1];  // [lists exported][colour][group size]
   unsigned seq = 0;  // completion stamp of the last fused frame (FrameResultHost::seq)
 
   // profiling of the integrate kernel
@@ -187,16 +196,23 @@ int check_kernel(tf_map* m, const char* what) {
 
 bool cam_ok(const tf_map* m, const tf_camera* c) { return c && c->width == m->W && c->height == m->H; }
 
-int find_slot(tf_map* m, int32_t frame_index) {
+// Slot of a stored frame, or -1.  for_compute: work is about to be queued on the compute stream
+// that reads the slot, so make that stream wait for the slot's uploads.
+int find_slot(tf_map* m, int32_t frame_index, bool for_compute = true) {
   auto it = m->frame_to_slot.find(frame_index);
   if (it == m->frame_to_slot.end()) return -1;
-  m->slots[it->second].last_use = ++m->use_clock;
+  FrameSlot& fsl = m->slots[it->second];
+  fsl.last_use = ++m->use_clock;
+  if (for_compute && fsl.pending) {
+    cudaStreamWaitEvent(m->stream, fsl.ready, 0);
+    fsl.pending = false;
+  }
   return it->second;
 }
 
 // Slot for frame_index: existing, free, or the least-recently-used one.
 int acquire_slot(tf_map* m, int32_t frame_index) {
-  int s = find_slot(m, frame_index);
+  int s = find_slot(m, frame_index, false);
   if (s >= 0) return s;
   int best = -1;
   for (int i = 0; i < (int)m->slots.size(); i++) {
@@ -213,12 +229,7 @@ int acquire_slot(tf_map* m, int32_t frame_index) {
 }
 
 int ensure_color_planes(tf_map* m, FrameSlot& s) {
-  if (!s.rgba) {
-    CUDA_OK(m, dmalloc(&s.rgba, (size_t)m->npix));
-    CUDA_OK(m, dmalloc(&s.quality, (size_t)m->npix));
-    CUDA_OK(m, dmalloc(&s.rgb, (size_t)m->npix * 3));
-    CUDA_OK(m, dmalloc(&s.valid, (size_t)m->npix));
-  }
+  if (!s.rgba) return fail(m, TF_ERR_INVALID, "map created with use_color = 0: no colour planes in the frame store");
   return TF_OK;
 }
 
@@ -405,19 +416,24 @@ void tf_host_free(void* p) {
 }
 
 static void destroy_graphs(tf_map* m) {
-  for (auto& row : m->graphs)
-    for (auto& fg : row) {
-      if (fg.exec) cudaGraphExecDestroy(fg.exec);
-      if (fg.graph) cudaGraphDestroy(fg.graph);
-      fg = FrameGraph{};
-    }
+  for (auto& plane : m->graphs)
+    for (auto& row : plane)
+      for (auto& fg : row) {
+        if (fg.exec) cudaGraphExecDestroy(fg.exec);
+        if (fg.graph) cudaGraphDestroy(fg.graph);
+        fg = FrameGraph{};
+      }
 }
 
 void tf_destroy(tf_map* m) {
   if (!m) return;
   cudaSetDevice(m->cfg.device);
   if (m->stream) cudaStreamSynchronize(m->stream);
+  if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
   destroy_graphs(m);
+  for (auto& sl : m->slots)
+    if (sl.ready) cudaEventDestroy(sl.ready);
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   cudaFree(m->md.table); cudaFree(m->md.pool); cudaFree(m->md.slot_id);
   cudaFree(m->md.slot_flags); cudaFree(m->md.free_stack); cudaFree(m->fs);
   cudaFree(m->cb.mask32); cudaFree(m->cb.local_off); cudaFree(m->cb.hit_items); cudaFree(m->cb.hit_count);
@@ -427,9 +443,9 @@ void tf_destroy(tf_map* m) {
   cudaFree(m->count_d); cudaFree(m->atlas); cudaFree(m->patch_d);
   cudaFreeHost(m->res_h); cudaFreeHost(m->out_ids_h); cudaFreeHost(m->out_new_h); cudaFreeHost(m->out_upd_h);
   cudaFreeHost(m->out_q_h); cudaFreeHost(m->upd_stage_h); cudaFreeHost(m->q_stage_h);
-  for (auto& s : m->slots) {
-    cudaFree(s.depth); cudaFree(s.rgba); cudaFree(s.quality); cudaFree(s.rgb); cudaFree(s.valid);
-  }
+  cudaFree(m->slab_depth);
+  cudaFree(m->slab_color);
+  cudaFree(m->st_ids); cudaFree(m->st_new); cudaFree(m->st_upd); cudaFree(m->st_q);
   for (auto& ep : m->ev_pool) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
   for (auto& ep : m->ev_pending) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
   if (m->stream) cudaStreamDestroy(m->stream);
@@ -507,6 +523,7 @@ int tf_create(tf_map** out, const tf_config* cfg) {
   C_OK(cudaGetDeviceProperties(&prop, cfg->device));
   m->sm_count = prop.multiProcessorCount;
   C_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  C_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   int occ = 1;
   C_OK(cudaFuncSetAttribute(integrate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)integrate_smem_bytes(kMaxGroupFrames)));
@@ -565,14 +582,34 @@ int tf_create(tf_map** out, const tf_config* cfg) {
   C_OK(cudaHostAlloc((void**)&m->q_stage_h, (size_t)m->list_cap * sizeof(float), cudaHostAllocDefault));
   memset(m->res_h, 0, sizeof(FrameResultHost));
   C_OK(cudaHostGetDevicePointer((void**)&m->res_d, m->res_h, 0));
+  C_OK(dmalloc(&m->st_ids, (size_t)m->list_cap));
+  C_OK(dmalloc(&m->st_new, (size_t)m->list_cap));
+  C_OK(dmalloc(&m->st_upd, (size_t)m->list_cap));
+  C_OK(dmalloc(&m->st_q, (size_t)m->list_cap));
   C_OK(cudaHostGetDevicePointer((void**)&m->out_ids_d, m->out_ids_h, 0));
   C_OK(cudaHostGetDevicePointer((void**)&m->out_new_d, m->out_new_h, 0));
   C_OK(cudaHostGetDevicePointer((void**)&m->out_upd_d, m->out_upd_h, 0));
   C_OK(cudaHostGetDevicePointer((void**)&m->out_q_d, m->out_q_h, 0));
 
   const int max_frames = cfg->max_frames > 0 ? cfg->max_frames : 32;
+  // The frame store is allocated up front as two slabs (16 B per pixel and slot with colour):
+  // cudaMalloc in the per-frame path would stall the stream for hundreds of microseconds.
   m->slots.resize(max_frames);
-  for (auto& s : m->slots) C_OK(dmalloc(&s.depth, (size_t)m->npix));
+  C_OK(dmalloc(&m->slab_depth, (size_t)m->npix * max_frames));
+  for (int i = 0; i < max_frames; i++) {
+    m->slots[i].depth = m->slab_depth + (size_t)i * m->npix;
+    C_OK(cudaEventCreateWithFlags(&m->slots[i].ready, cudaEventDisableTiming));
+  }
+  if (cfg->use_color) {
+    C_OK(cudaMalloc((void**)&m->slab_color, (size_t)m->npix * 12 * max_frames));
+    for (int i = 0; i < max_frames; i++) {
+      unsigned char* base = m->slab_color + (size_t)i * m->npix * 12;
+      m->slots[i].rgba = reinterpret_cast<uchar4*>(base);
+      m->slots[i].quality = reinterpret_cast<float*>(base + (size_t)m->npix * 4);
+      m->slots[i].rgb = base + (size_t)m->npix * 8;
+      m->slots[i].valid = base + (size_t)m->npix * 11;
+    }
+  }
 
   // Atlas::SetResolution (Structure/Atlas.h:62-65)
   m->patch_w = (int)std::floor(4800 * cfg->voxel_res);
@@ -592,6 +629,7 @@ int tf_reset(tf_map* m) {
 
 int tf_sync(tf_map* m) {
   if (!m) return TF_ERR_INVALID;
+  CUDA_OK(m, cudaStreamSynchronize(m->copy_stream));
   CUDA_OK(m, cudaStreamSynchronize(m->stream));
   prof_collect(m, 0);
   return TF_OK;
@@ -607,40 +645,44 @@ int tf_upload_frame(tf_map* m, int32_t frame_index, const float* depth, const ui
   const int s = acquire_slot(m, frame_index);
   FrameSlot& fsl = m->slots[s];
   const size_t nb = (size_t)m->npix * 4;
-  CUDA_OK(m, cudaMemcpyAsync(fsl.depth, depth, nb, cudaMemcpyHostToDevice, m->stream));
+  CUDA_OK(m, cudaMemcpyAsync(fsl.depth, depth, nb, cudaMemcpyHostToDevice, m->copy_stream));
   m->counters.h2d_bytes += nb;
   if (rgba || quality) {
     if (int rc = ensure_color_planes(m, fsl)) return rc;
   }
   if (rgba) {
-    CUDA_OK(m, cudaMemcpyAsync(fsl.rgba, rgba, nb, cudaMemcpyHostToDevice, m->stream));
+    CUDA_OK(m, cudaMemcpyAsync(fsl.rgba, rgba, nb, cudaMemcpyHostToDevice, m->copy_stream));
     m->counters.h2d_bytes += nb;
     fsl.has_rgba = true;
   }
   if (quality) {
-    CUDA_OK(m, cudaMemcpyAsync(fsl.quality, quality, nb, cudaMemcpyHostToDevice, m->stream));
+    CUDA_OK(m, cudaMemcpyAsync(fsl.quality, quality, nb, cudaMemcpyHostToDevice, m->copy_stream));
     m->counters.h2d_bytes += nb;
     fsl.has_quality = true;
   }
+  CUDA_OK(m, cudaEventRecord(fsl.ready, m->copy_stream));
+  fsl.pending = true;
   return TF_OK;
 }
 
 int tf_upload_keyframe_rgb(tf_map* m, int32_t frame_index, const uint8_t* rgb, const uint8_t* color_valid) {
   if (!m || !rgb) return fail(m, TF_ERR_INVALID, "tf_upload_keyframe_rgb: bad argument");
-  const int s = find_slot(m, frame_index);
+  const int s = find_slot(m, frame_index, false);
   if (s < 0) return fail(m, TF_ERR_NOT_FOUND, "frame_index not in the frame store (upload depth first)");
   FrameSlot& fsl = m->slots[s];
   if (int rc = ensure_color_planes(m, fsl)) return rc;
-  CUDA_OK(m, cudaMemcpyAsync(fsl.rgb, rgb, (size_t)m->npix * 3, cudaMemcpyHostToDevice, m->stream));
+  CUDA_OK(m, cudaMemcpyAsync(fsl.rgb, rgb, (size_t)m->npix * 3, cudaMemcpyHostToDevice, m->copy_stream));
   m->counters.h2d_bytes += (int64_t)m->npix * 3;
   if (color_valid) {
-    CUDA_OK(m, cudaMemcpyAsync(fsl.valid, color_valid, (size_t)m->npix, cudaMemcpyHostToDevice, m->stream));
+    CUDA_OK(m, cudaMemcpyAsync(fsl.valid, color_valid, (size_t)m->npix, cudaMemcpyHostToDevice, m->copy_stream));
     m->counters.h2d_bytes += m->npix;
   }
-  pack_rgba_kernel<<<m->grid, kThreads, 0, m->stream>>>(fsl.rgb, color_valid ? fsl.valid : nullptr, fsl.rgba, m->npix);
+  pack_rgba_kernel<<<m->grid, kThreads, 0, m->copy_stream>>>(fsl.rgb, color_valid ? fsl.valid : nullptr, fsl.rgba, m->npix);
   if (int rc = check_kernel(m, "pack_rgba_kernel")) return rc;
   fsl.has_rgb = true;
   fsl.has_rgba = true;
+  CUDA_OK(m, cudaEventRecord(fsl.ready, m->copy_stream));
+  fsl.pending = true;
   return TF_OK;
 }
 
@@ -764,7 +806,14 @@ struct FrameArgs {
   FusedFinalize ff;
   const int* n_dev;
   int n_host;
+  bool want_export;
+  ExportArgs ex;
 };
+
+static int export_grid(const tf_map* m) {
+  static const int g = [] { const char* e = getenv("TEXFUSION_B200_EXPORT_GRID"); return e ? atoi(e) : 0; }();
+  return g > 0 ? g : m->sm_count;
+}
 
 static void launch_frame_kernels(tf_map* m, FrameArgs& a) {
   bbox_kernel<<<m->grid, kThreads, 0, m->stream>>>(a.cp, a.depth, m->fs, a.parity);
@@ -778,6 +827,15 @@ static void launch_frame_kernels(tf_map* m, FrameArgs& a) {
     launch_pdl(integrate_kernel<false>, m->grid_integrate, integrate_smem_bytes(a.gp.n_frames), m->stream, a.gp, m->md,
                (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, a.n_dev,
                a.n_host, &m->fs->work_next, m->list_upd, m->list_q, a.ff);
+  if (a.want_export) launch_pdl(export_kernel, export_grid(m), 0, m->stream, a.ex);
+}
+
+// Device-visible alias of a page-locked, 16-byte aligned host pointer (else nullptr).
+static void* device_alias(const void* p) {
+  if (!p || ((uintptr_t)p & 15u)) return nullptr;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
 static bool graphs_enabled() {  // on by default; TEXFUSION_B200_GRAPH=0 uses plain launches
@@ -797,16 +855,19 @@ static bool build_frame_graph(tf_map* m, FrameGraph& fg, FrameArgs& a) {
   if (cudaGraphInstantiate(&fg.exec, g, 0) != cudaSuccess) { cudaGetLastError(); return false; }
   cudaGraphNode_t nodes[8];
   size_t nn = 8;
-  if (cudaGraphGetNodes(g, nodes, &nn) != cudaSuccess || nn != 3) { cudaGetLastError(); return false; }
-  const void* fn[3] = {(const void*)bbox_kernel, (const void*)cull_kernel<true>,
-                       a.any_color ? (const void*)integrate_kernel<true> : (const void*)integrate_kernel<false>};
+  const size_t n_expected = a.want_export ? 4 : 3;
+  if (cudaGraphGetNodes(g, nodes, &nn) != cudaSuccess || nn != n_expected) { cudaGetLastError(); return false; }
+  const void* fn[4] = {(const void*)bbox_kernel, (const void*)cull_kernel<true>,
+                       a.any_color ? (const void*)integrate_kernel<true> : (const void*)integrate_kernel<false>,
+                       (const void*)export_kernel};
   for (size_t i = 0; i < nn; i++) {
     cudaKernelNodeParams kp{};
     if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) { cudaGetLastError(); return false; }
-    for (int k = 0; k < 3; k++)
+    for (size_t k = 0; k < n_expected; k++)
       if (kp.func == fn[k]) { fg.node[k] = nodes[i]; fg.kp[k] = kp; }
   }
-  if (!fg.node[0] || !fg.node[1] || !fg.node[2]) return false;
+  for (size_t k = 0; k < n_expected; k++)
+    if (!fg.node[k]) return false;
   fg.failed = false;
   return true;
 }
@@ -821,9 +882,11 @@ static int launch_frame_graph(tf_map* m, FrameGraph& fg, FrameArgs& a) {
   void* p_cull[] = {&a.cp, &a.gp, &m->md, &a.depth, &m->fs, &m->cb, &m->cfg.n_ranks, &m->cfg.rank, &a.parity, &a.want_order};
   void* p_int[] = {&a.gp, &m->md, &list_slots, &list_hpos, &list_setup, &a.n_dev, &a.n_host, &work_next, &m->list_upd,
                    &m->list_q, &a.ff};
-  void** params[3] = {p_bbox, p_cull, p_int};
+  void* p_exp[] = {&a.ex};
+  void** params[4] = {p_bbox, p_cull, p_int, p_exp};
+  const int n_nodes = a.want_export ? 4 : 3;
   HT(2);
-  for (int k = 0; k < 3; k++) {
+  for (int k = 0; k < n_nodes; k++) {
     fg.kp[k].kernelParams = params[k];
     fg.kp[k].extra = nullptr;
     CUDA_OK(m, cudaGraphExecKernelNodeSetParams(fg.exec, fg.node[k], &fg.kp[k]));
@@ -831,7 +894,7 @@ static int launch_frame_graph(tf_map* m, FrameGraph& fg, FrameArgs& a) {
   HT(3);
   CUDA_OK(m, cudaGraphLaunch(fg.exec, m->stream));
   HT(4);
-  m->counters.kernel_launches += 3;
+  m->counters.kernel_launches += n_nodes;
   return TF_OK;
 }
 
@@ -881,16 +944,34 @@ static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, co
   ff.ordered = want_lists ? 1 : 0;
   ff.fs = m->fs;
   ff.cb = m->cb;
-  ff.ids_out = ids_out ? m->out_ids_d : nullptr;
-  ff.new_out = new_out ? m->out_new_d : nullptr;
-  ff.upd_out = upd_out ? m->out_upd_d : nullptr;
-  ff.q_out = q_out ? m->out_q_d : nullptr;
+  ff.ids_out = ids_out ? m->st_ids : nullptr;
+  ff.new_out = new_out ? m->st_new : nullptr;
+  ff.upd_out = upd_out ? m->st_upd : nullptr;
+  ff.q_out = q_out ? m->st_q : nullptr;
   ff.out_cap = ocap;
   ff.res = m->res_d;
   ff.seq = ++m->seq;
+  ff.export_follows = want_lists ? 1 : 0;
+  // Lists go straight into the caller's buffers when those are page-locked (tf_host_alloc) and
+  // 16-byte aligned, else through the map's own mapped staging buffers + a host copy.
+  a.want_export = want_lists;
+  ExportArgs& ex = a.ex;
+  ex = ExportArgs{};
+  void* direct[4] = {device_alias(ids_out), device_alias(new_out), device_alias(upd_out), device_alias(q_out)};
+  if (want_lists) {
+    ex.ids_s = ff.ids_out, ex.new_s = ff.new_out, ex.upd_s = ff.upd_out, ex.q_s = ff.q_out;
+    ex.ids_h = ids_out ? (direct[0] ? (int3*)direct[0] : m->out_ids_d) : nullptr;
+    ex.new_h = new_out ? (direct[1] ? (unsigned char*)direct[1] : m->out_new_d) : nullptr;
+    ex.upd_h = upd_out ? (direct[2] ? (unsigned char*)direct[2] : m->out_upd_d) : nullptr;
+    ex.q_h = q_out ? (direct[3] ? (float*)direct[3] : m->out_q_d) : nullptr;
+    ex.cap = ocap;
+    ex.fs = m->fs;
+    ex.res = m->res_d;
+    ex.seq = ff.seq;
+  }
 
   // bbox -> cull (+ HasChunk / CreateChunk) -> integrate (+ Finalize, garbage collection, publication)
-  FrameGraph& fg = m->graphs[a.any_color ? 1 : 0][n_frames];
+  FrameGraph& fg = m->graphs[want_lists ? 1 : 0][a.any_color ? 1 : 0][n_frames];
   bool launched = false;
   if (m->prof == 0 && graphs_enabled() && (fg.exec || build_frame_graph(m, fg, a)) && !fg.failed) {
     m->parity ^= 1;
@@ -904,6 +985,10 @@ static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, co
     if (int rc = launch_cull(m, a.cp, a.gp, a.depth, true, want_lists)) return rc;
     a.parity = m->parity;
     if (int rc = launch_integrate(m, a.gp, a.n_dev, 0, -1, &ff)) return rc;
+    if (a.want_export) {
+      launch_pdl(export_kernel, export_grid(m), 0, m->stream, a.ex);
+      if (int rc = check_kernel(m, "export_kernel")) return rc;
+    }
     HT(5);
     CUDA_OK(m, cudaStreamSynchronize(m->stream));
   }
@@ -912,10 +997,10 @@ static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, co
   const FrameResultHost r = *m->res_h;
   prof_collect(m, algorithmic_bytes(m, r.n_chunks, color, n_frames));
   const int64_t nout = std::min<int64_t>(r.n_chunks, ocap);
-  if (ids_out) memcpy(ids_out, m->out_ids_h, (size_t)nout * sizeof(int3));
-  if (new_out) memcpy(new_out, m->out_new_h, (size_t)nout);
-  if (upd_out) memcpy(upd_out, m->out_upd_h, (size_t)nout);
-  if (q_out) memcpy(q_out, m->out_q_h, (size_t)nout * sizeof(float));
+  if (ids_out && !direct[0]) memcpy(ids_out, m->out_ids_h, (size_t)nout * sizeof(int3));
+  if (new_out && !direct[1]) memcpy(new_out, m->out_new_h, (size_t)nout);
+  if (upd_out && !direct[2]) memcpy(upd_out, m->out_upd_h, (size_t)nout);
+  if (q_out && !direct[3]) memcpy(q_out, m->out_q_h, (size_t)nout * sizeof(float));
   m->counters.d2h_bytes += sizeof(FrameResultHost) + nout * ((ids_out ? 12 : 0) + (new_out ? 1 : 0) + (upd_out ? 1 : 0) + (q_out ? 4 : 0));
   if (stats) {
     stats->n_chunks = r.n_chunks;

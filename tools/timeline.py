@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--lists", action="store_true", help="request the ordered chunk lists (as the e2e leg of bench.py does)")
     ap.add_argument("--flush-read", action="store_true", help="after the write flush, read a second buffer (clean L2 lines)")
     args = ap.parse_args()
     cam = synth.Camera()
@@ -47,6 +48,10 @@ def main():
     traces2 = []
     traces = []
     rows = []
+    o_ids = np.empty((m.list_cap, 3), np.int32)
+    o_new = np.empty(m.list_cap, np.uint8)
+    o_upd = np.empty(m.list_cap, np.uint8)
+    o_q = np.empty(m.list_cap, np.float32)
     cnt = []
     walls = []
     for i, fr in enumerate(seq.frames):
@@ -58,8 +63,14 @@ def main():
         torch.cuda.synchronize()
         L.tf_debug_timeline(m.h, None, 1)
         t0 = time.perf_counter()
-        rc = L.tf_integrate_frame(m.h, fr.index, int(fr.is_keyframe), C.byref(pose), C.byref(camc), C.byref(st),
-                                  None, None, None, None, 0)
+        if args.lists:
+            vp = C.c_void_p
+            rc = L.tf_integrate_frame(m.h, fr.index, int(fr.is_keyframe), C.byref(pose), C.byref(camc), C.byref(st),
+                                      o_ids.ctypes.data_as(vp), o_new.ctypes.data_as(vp), o_upd.ctypes.data_as(vp),
+                                      o_q.ctypes.data_as(vp), m.list_cap)
+        else:
+            rc = L.tf_integrate_frame(m.h, fr.index, int(fr.is_keyframe), C.byref(pose), C.byref(camc), C.byref(st),
+                                      None, None, None, None, 0)
         t1 = time.perf_counter()
         assert rc == 0
         L.tf_debug_timeline(m.h, out, 0)
@@ -89,7 +100,7 @@ def main():
         rows.append(t / 1e3)
         walls.append((t1 - t0) * 1e6)
     r = np.nanmean(np.stack(rows), axis=0)
-    names = ["bbox", "cull", "alloc", "integrate"]
+    names = ["bbox", "cull", "export", "integrate"]
     print(f"{'kernel':10s} {'start':>8s} {'waited':>8s} {'work end':>9s} {'end':>8s}   (us after bbox start, mean of {len(rows)} frames)")
     for k in range(4):
         print(f"{names[k]:10s} {r[k,0]:8.2f} {r[k,1]:8.2f} {r[k,2]:9.2f} {r[k,3]:8.2f}")
