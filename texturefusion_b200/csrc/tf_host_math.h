@@ -80,6 +80,7 @@ inline void make_frame_dev(const tf_pose& pose, const tf_camera& cam, int flag, 
   f.fx = (float)(int)cam.fx, f.fy = (float)(int)cam.fy;
   f.cxh = (float)((double)cx + 0.5);  // double add, rounded to float by _mm256_set1_ps
   f.cyh = (float)((double)cy + 0.5);
+  f.eps_u = proj_eps_abs(f.cxh), f.eps_v = proj_eps_abs(f.cyh);
   f.W = cam.width, f.H = cam.height;
   f.near_p = cam.near_plane, f.far_p = cam.far_plane;
   f.flag = flag;
