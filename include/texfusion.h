@@ -14,10 +14,19 @@
  *   - every function returns 0 on success, <0 on error (tf_last_error gives the text);
  *     functions that are pure queries say so.
  *   - a tf_map is not thread-safe; one caller thread at a time (the reference's map
- *     thread, GCFusion/MobileFusion.cpp:99-112).  All device work of one map runs on one
- *     CUDA stream; a call returns once the results it hands to the host are visible.
- *   - image pointers are borrowed for the duration of the call.  Pinned host memory
- *     (tf_host_alloc) is DMA'd directly; pageable memory is staged.
+ *     thread, GCFusion/MobileFusion.cpp:99-112).  Kernels and read-backs of one map run on one
+ *     CUDA stream, frame uploads on a second (copy) stream; a call returns once the results
+ *     it hands to the host are visible.
+ *   - tf_upload_frame / tf_upload_keyframe_rgb are asynchronous: pageable sources are staged
+ *     before the call returns; page-locked sources (tf_host_alloc) are DMA'd directly and
+ *     must stay untouched until a call that consumes that frame has returned, or tf_sync.
+ *     A caller can therefore upload frame i+1 and then fuse frame i: the copy overlaps the
+ *     kernels.
+ *   - output arrays that are page-locked (tf_host_alloc / cudaHostAlloc / cudaHostRegister)
+ *     and 16-byte aligned are written by the device directly; any other pointer goes through
+ *     an internal staging buffer and a host copy (same results, a few microseconds more).
+ *   - environment: TEXFUSION_B200_GRAPH=0 (plain kernel launches instead of a CUDA graph per
+ *     frame), TEXFUSION_B200_PDL=0 (no programmatic dependent launch).
  *   - there is NO CPU fallback: without a CUDA device tf_create fails with TF_ERR_CUDA.
  */
 #ifndef TEXFUSION_B200_H
@@ -72,7 +81,8 @@ typedef struct {
   int32_t device;         /* CUDA ordinal */
   int32_t n_ranks, rank;  /* chunk sharding: this map owns chunks with owner(id) == rank */
   int64_t max_chunks;     /* chunk-pool capacity (8 KiB each); 0 = default */
-  int32_t max_frames;     /* frame-store slots; 0 = default */
+  int32_t max_frames;     /* frame-store slots, allocated up front: 4 B (16 B with use_color) per
+                             pixel and slot; 0 = default (32) */
   int32_t width, height;  /* frame size of the store; 0 = 640x480 */
 } tf_config;
 
