@@ -409,3 +409,58 @@ def test_full_size_round_trip_properties():
         g.integrate(kf.index, True, kf.pose, cam, ids, 0)
     s0, w0, c0 = g.download_chunks(ids)
     assert np.all(w0 == 0) and np.all(s0[seen] == 999.0) and not c0.any()
+
+
+@pytest.mark.parametrize("res", (0.02, 0.005))
+def test_fused_frame_output_paths_agree(res):
+    """The fused call must give the same map and the same ordered lists whichever way the results
+    travel: CUDA graph + completion stamp or plain launches (profiling level 1 forces those),
+    lists exported straight into page-locked caller buffers, through the staging buffers into
+    pageable arrays, or not requested at all; the next frame's upload may be in flight (copy
+    stream) while a frame is fused."""
+    import ctypes as C
+    seq = room_sequence(6)
+    cam = seq.cam
+    o = OracleMap(res)
+    variants = {"graph+pageable": capi.Map(res), "plain+pageable": capi.Map(res), "graph+pinned": capi.Map(res),
+                "graph, no lists": capi.Map(res)}
+    variants["plain+pageable"].set_profiling(1)
+    cap = 1 << 16
+    pins = [capi.PinnedBuffer((cap, 3), np.int32), capi.PinnedBuffer((cap,), np.uint8), capi.PinnedBuffer((cap,), np.uint8),
+            capi.PinnedBuffer((cap,), np.float32)]
+    vp = C.c_void_p
+    frames = seq.frames
+
+    def upload(m, fr):
+        m.upload_frame(fr.index, fr.depth, fr.rgba() if fr.is_keyframe else None, fr.quality if fr.is_keyframe else None)
+
+    for m in variants.values():
+        upload(m, frames[0])
+    for i, fr in enumerate(frames):
+        rgba = fr.rgba() if fr.is_keyframe else None
+        o_ids, o_new = o.prepare(fr.depth, fr.pose, cam)
+        o_upd, _ = o.integrate(fr.depth, rgba, fr.quality if fr.is_keyframe else None, fr.pose, cam, o_ids, 1, -1)
+        o.finalize(o_ids, o_upd, o_new)
+        for name, m in variants.items():
+            if i + 1 < len(frames):
+                upload(m, frames[i + 1])  # in flight during this frame's kernels
+            if name == "graph+pinned":
+                st = capi.FrameStats()
+                rc = m.L.tf_integrate_frame(m.h, fr.index, int(fr.is_keyframe), C.byref(capi.make_pose(fr.pose)),
+                                            C.byref(capi.make_camera(cam)), C.byref(st), vp(pins[0].ptr), vp(pins[1].ptr),
+                                            vp(pins[2].ptr), vp(pins[3].ptr), cap)
+                assert rc == 0, m.L.tf_last_error(m.h)
+                n = st.n_chunks
+                ids, new, upd = pins[0].array[:n], pins[1].array[:n], pins[2].array[:n]
+            elif name == "graph, no lists":
+                st, *_ = m.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam, want_lists=False)
+                assert st.n_chunks == len(o_ids), name
+                continue
+            else:
+                st, ids, new, upd, q = m.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam)
+            assert np.array_equal(ids, o_ids), f"{name}: frame {i} list order"
+            assert np.array_equal(new != 0, np.asarray(o_new) != 0), f"{name}: frame {i} is_new"
+            assert np.array_equal(upd != 0, np.asarray(o_upd) != 0), f"{name}: frame {i} updated"
+    for name, m in variants.items():
+        assert assert_maps_equal(m, o, what=name)
+        m.close()
