@@ -307,7 +307,7 @@ def main():
     # and the D2H read of its results (frame statistics + the ordered chunk lists, written into
     # page-locked output buffers).  The loop is double buffered the way a streaming caller would
     # write it: tf_upload_frame(i+1) is issued before tf_integrate_frame(i), so the copy of the next
-    # frame overlaps the kernels of the current one; tf_sync at the end of the step makes sure that
+    # frame overlaps the kernels of the current one; tf_wait_upload at the end of the step makes sure that
     # copy has finished inside the timed region.
     m = capi.Map(args.res, device=local_rank, n_ranks=world, rank=rank, max_frames=32, max_chunks=1 << 19)
     pin_d = [capi.PinnedBuffer((cam.height, cam.width), np.float32) for _ in range(nf)]
@@ -354,9 +354,10 @@ def main():
                 dist.broadcast(t, src=0)
             torch.cuda.synchronize()
             return fuse(i)
-        upload((i + 1) % nf)  # next frame's copy, in flight during this frame's kernels
+        j = (i + 1) % nf
+        upload(j)  # next frame's copy, in flight during this frame's kernels
         n = fuse(i)
-        rc = L.tf_sync(m.h)
+        rc = L.tf_wait_upload(m.h, frames[j].index)  # ... and finished inside this timed step
         assert rc == 0
         return n
 
@@ -387,7 +388,7 @@ def main():
            "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / args.steps,
            "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / args.steps,
            "ms_per_step": 1e3 * e2e_s / args.steps, "median_ms_per_step": 1e3 * float(np.median(step_s)),
-           "mode": "double buffered: upload(i+1) | fuse(i) | sync, host buffers page-locked"}
+           "mode": "double buffered: upload(i+1) | fuse(i) | wait_upload(i+1), host buffers page-locked"}
     m.close()
 
     if rank != 0:

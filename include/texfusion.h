@@ -237,6 +237,9 @@ int tf_patch_texcoords(tf_map* m, int32_t frame_index, const tf_pose* world_to_c
 
 /* ---- misc ---------------------------------------------------------------------------- */
 int tf_sync(tf_map* m);
+/* Blocks until the uploads of one stored frame have completed (its page-locked source buffers may
+ * then be reused); cheaper than tf_sync.  TF_ERR_NOT_FOUND if the frame is not in the store. */
+int tf_wait_upload(tf_map* m, int32_t frame_index);
 /* counters since creation: kernels launched by this library, bytes moved each way */
 typedef struct {
   int64_t kernel_launches;

@@ -635,6 +635,18 @@ int tf_sync(tf_map* m) {
   return TF_OK;
 }
 
+int tf_wait_upload(tf_map* m, int32_t frame_index) {
+  if (!m) return TF_ERR_INVALID;
+  const int s = find_slot(m, frame_index, false);
+  if (s < 0) return fail(m, TF_ERR_NOT_FOUND, "frame_index not in the frame store");
+  // (the slot stays `pending` for the compute stream: waiting on a completed event costs nothing)
+  for (;;) {  // polling the event returns earlier than cudaEventSynchronize's wake-up
+    const cudaError_t e = cudaEventQuery(m->slots[s].ready);
+    if (e == cudaSuccess) return TF_OK;
+    if (e != cudaErrorNotReady) return fail(m, TF_ERR_CUDA, cudaGetErrorString(e));
+  }
+}
+
 void* tf_stream(tf_map* m) { return m ? (void*)m->stream : nullptr; }
 
 // ---- frame store ---------------------------------------------------------------------------
