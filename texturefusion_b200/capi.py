@@ -299,9 +299,10 @@ class Map:
             return st, ids[:n].copy(), new[:n].copy(), upd[:n].copy(), q[:n].copy()
         return st, None, None, None, None
 
-    def integrate_batch(self, items, cam):
-        """items: list of dicts {flag, frames:[(frame_index,use_color,pose)], ids (flag 0)}.
-        Returns, per item, None (flag 0) or (valid_ids, quality) (flag 1)."""
+    def marshal_batch(self, items, cap=None):
+        """Builds the tf_batch_item array of integrate_batch (kept separate so that a benchmark can
+        time the C call alone).  Returns an opaque tuple for run_batch."""
+        cap = cap or self.list_cap
         n = len(items)
         arr = (BatchItem * n)()
         keep, outs = [], []
@@ -320,17 +321,26 @@ class Map:
                 arr[k].n_ids = len(ids)
                 outs.append(None)
             else:
-                valid = np.empty((self.list_cap, 3), np.int32)
-                q = np.empty(self.list_cap, np.float32)
+                valid = np.empty((cap, 3), np.int32)
+                q = np.empty(cap, np.float32)
                 nv = C.c_int64(0)
                 keep += [valid, q, nv]
                 arr[k].valid_out = valid.ctypes.data
                 arr[k].quality_out = q.ctypes.data
-                arr[k].cap = self.list_cap
+                arr[k].cap = cap
                 arr[k].n_valid_out = C.pointer(nv)
                 outs.append((valid, q, nv))
+        return arr, n, keep, outs
+
+    def run_batch(self, marshalled, cam):
+        arr, n, _keep, outs = marshalled
         self._check(self.L.tf_integrate_batch(self.h, arr, n, C.byref(make_camera(cam))))
         return [None if o is None else (o[0][:o[2].value].copy(), o[1][:o[2].value].copy()) for o in outs]
+
+    def integrate_batch(self, items, cam):
+        """items: list of dicts {flag, frames:[(frame_index,use_color,pose)], ids (flag 0)}.
+        Returns, per item, None (flag 0) or (valid_ids, quality) (flag 1)."""
+        return self.run_batch(self.marshal_batch(items), cam)
 
     # queries -------------------------------------------------------------------------------
     def has_chunk(self, id3) -> bool:

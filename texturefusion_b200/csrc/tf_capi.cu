@@ -91,6 +91,13 @@ struct tf_map {
   unsigned char* out_new_h = nullptr;
   unsigned char* out_upd_h = nullptr;
   float* out_q_h = nullptr;
+  // tf_integrate_batch: result arena in mapped page-locked memory (allocated by the first batch)
+  int3* arena_ids = nullptr;
+  float* arena_q = nullptr;
+  unsigned char* arena_upd = nullptr;
+  int2* batch_rec = nullptr;
+  int3* ids_stage = nullptr;     // page-locked staging of the de-integration lists (pageable sources would
+  int64_t ids_stage_used = 0;    // make cudaMemcpyAsync wait for the stream, i.e. serialise host and device)
   int3* st_ids = nullptr;  // device staging of the ordered per-chunk outputs (export_kernel)
   unsigned char* st_new = nullptr;
   unsigned char* st_upd = nullptr;
@@ -446,6 +453,8 @@ void tf_destroy(tf_map* m) {
   cudaFree(m->slab_depth);
   cudaFree(m->slab_color);
   cudaFree(m->st_ids); cudaFree(m->st_new); cudaFree(m->st_upd); cudaFree(m->st_q);
+  cudaFreeHost(m->arena_ids); cudaFreeHost(m->arena_q); cudaFreeHost(m->arena_upd); cudaFreeHost(m->batch_rec);
+  cudaFreeHost(m->ids_stage);
   for (auto& ep : m->ev_pool) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
   for (auto& ep : m->ev_pending) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
   if (m->stream) cudaStreamDestroy(m->stream);
@@ -827,10 +836,12 @@ static int export_grid(const tf_map* m) {
   return g > 0 ? g : m->sm_count;
 }
 
-static void launch_frame_kernels(tf_map* m, FrameArgs& a) {
+static void launch_frame_kernels(tf_map* m, FrameArgs& a, bool profile = false) {
   bbox_kernel<<<m->grid, kThreads, 0, m->stream>>>(a.cp, a.depth, m->fs, a.parity);
   launch_pdl(cull_kernel<true>, m->grid_cull, 0, m->stream, a.cp, a.gp, m->md, a.depth, m->fs, m->cb, m->cfg.n_ranks,
              m->cfg.rank, a.parity, a.want_order);
+  EventPair ep;
+  if (profile) prof_begin(m, ep);
   if (a.any_color)
     launch_pdl(integrate_kernel<true>, m->grid_integrate_c, integrate_smem_bytes(a.gp.n_frames), m->stream, a.gp, m->md,
                (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, a.n_dev,
@@ -839,7 +850,9 @@ static void launch_frame_kernels(tf_map* m, FrameArgs& a) {
     launch_pdl(integrate_kernel<false>, m->grid_integrate, integrate_smem_bytes(a.gp.n_frames), m->stream, a.gp, m->md,
                (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, a.n_dev,
                a.n_host, &m->fs->work_next, m->list_upd, m->list_q, a.ff);
+  if (profile) prof_end(m, ep);
   if (a.want_export) launch_pdl(export_kernel, export_grid(m), 0, m->stream, a.ex);
+  m->counters.kernel_launches += a.want_export ? 4 : 3;
 }
 
 // Device-visible alias of a page-locked, 16-byte aligned host pointer (else nullptr).
@@ -980,6 +993,7 @@ static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, co
     ex.fs = m->fs;
     ex.res = m->res_d;
     ex.seq = ff.seq;
+    ex.batch_item = -1;
   }
 
   // bbox -> cull (+ HasChunk / CreateChunk) -> integrate (+ Finalize, garbage collection, publication)
@@ -1039,44 +1053,177 @@ int tf_integrate_frame(tf_map* m, int32_t frame_index, int use_color, const tf_p
   return fused_group(m, &g, 1, cam, stats, ids_out, is_new_out, updated_out, quality_out, cap);
 }
 
+// ---- loop-closure batches ---------------------------------------------------------------------------
+//
+// All items of a batch are queued without intermediate host synchronisation: de-integration =
+// id upload + lookup + integrate; re-integration = the fused chain, whose ordered lists go to a
+// slice of a result arena in mapped host memory (export_kernel, batch mode).  The host synchronises
+// once per sub-batch and then derives every item's valid list (updated chunks, in list order).
+
+constexpr int kArenaCap = 1 << 22;     // list entries per sub-batch
+constexpr int kSubBatch = 32;          // re-integration items per synchronisation
+constexpr int64_t kIdsStage = 1 << 20; // staged de-integration ids per synchronisation
+
+static int ensure_arena(tf_map* m) {
+  if (m->arena_ids) return TF_OK;
+  CUDA_OK(m, cudaHostAlloc((void**)&m->arena_ids, (size_t)kArenaCap * sizeof(int3), cudaHostAllocMapped));
+  CUDA_OK(m, cudaHostAlloc((void**)&m->arena_q, (size_t)kArenaCap * sizeof(float), cudaHostAllocMapped));
+  CUDA_OK(m, cudaHostAlloc((void**)&m->arena_upd, (size_t)kArenaCap, cudaHostAllocMapped));
+  CUDA_OK(m, cudaHostAlloc((void**)&m->batch_rec, (size_t)kSubBatch * sizeof(int2), cudaHostAllocMapped));
+  CUDA_OK(m, cudaHostAlloc((void**)&m->ids_stage, (size_t)kIdsStage * sizeof(int3), cudaHostAllocDefault));
+  return TF_OK;
+}
+
+struct PendingItem {
+  const tf_batch_item* it;
+  int rec;          // index into batch_rec
+  int n_frames;
+  bool color[kMaxGroupFrames];
+  size_t first_event, n_events;  // profiling events of this item (m->ev_pending)
+};
+
+// synchronise, then hand the queued re-integration items their valid lists
+static int flush_batch(tf_map* m, std::vector<PendingItem>& pend) {
+  publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);  // error bits and allocator state of the whole sub-batch
+  if (int rc = check_kernel(m, "publish_kernel")) return rc;
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  absorb_result(m);
+  const int dev_err = m->res_h->error;
+  int rc = TF_OK;
+  for (const PendingItem& p : pend) {
+    const int2 r = m->batch_rec[p.rec];
+    if (r.x < 0) { rc = fail(m, TF_ERR_CAPACITY, "tf_integrate_batch: result arena exhausted"); continue; }
+    const int3* ids = m->arena_ids + r.y;
+    const float* q = m->arena_q + r.y;
+    const unsigned char* upd = m->arena_upd + r.y;
+    int64_t nv = 0;
+    for (int i = 0; i < r.x; i++) {
+      if (!upd[i]) continue;
+      if (nv < p.it->cap) {
+        if (p.it->valid_out) memcpy(&p.it->valid_out[nv], &ids[i], sizeof(int3));
+        if (p.it->quality_out) p.it->quality_out[nv] = q[i];
+      }
+      nv++;
+    }
+    if (p.it->n_valid_out) *p.it->n_valid_out = nv;
+    if (nv > p.it->cap && p.it->valid_out) rc = fail(m, TF_ERR_CAPACITY, "tf_integrate_batch: valid_out too small");
+    m->counters.d2h_bytes += (int64_t)r.x * 17;
+    m->counters.frames_integrated += p.n_frames;
+    m->counters.voxel_updates += (int64_t)r.x * 512 * p.n_frames;
+    for (size_t e = p.first_event; e < p.first_event + p.n_events && e < m->ev_pending.size(); e++)
+      m->ev_pending[e].bytes = algorithmic_bytes(m, r.x, p.color, p.n_frames);
+  }
+  pend.clear();
+  m->ids_stage_used = 0;
+  prof_collect(m, 0);
+  if (int rc2 = dev_error_to_code(m, dev_err)) return rc2;
+  return rc;
+}
+
 int tf_integrate_batch(tf_map* m, const tf_batch_item* items, int64_t n_items, const tf_camera* cam) {
   if (!m || n_items < 0 || (n_items > 0 && !items) || !cam_ok(m, cam))
     return fail(m, TF_ERR_INVALID, "tf_integrate_batch: bad argument");
-  std::vector<tf_chunk_id> ids;
-  std::vector<uint8_t> upd;
-  std::vector<float> q;
+  int max_frames = 1;
+  for (int64_t k = 0; k < n_items; k++) {
+    if (!items[k].frames || items[k].n_frames < 1 || items[k].n_frames > kMaxGroupFrames)
+      return fail(m, TF_ERR_INVALID, "tf_integrate_batch: group size must be 1..8");
+    if (items[k].flag == 0 && (items[k].n_ids < 0 || (items[k].n_ids > 0 && !items[k].ids)))
+      return fail(m, TF_ERR_INVALID, "tf_integrate_batch: de-integration item without a chunk list");
+    max_frames = std::max(max_frames, items[k].n_frames);
+  }
+  if (int rc = ensure_arena(m)) return rc;
+  if (int rc = ensure_setup(m, max_frames)) return rc;
+  CUDA_OK(m, cudaMemsetAsync(&m->fs->arena_off, 0, sizeof(int), m->stream));
+  std::vector<PendingItem> pend;
+  tf_group_frame fr[kMaxGroupFrames];
   for (int64_t k = 0; k < n_items; k++) {
     const tf_batch_item& it = items[k];
-    if (!it.frames || it.n_frames < 1) return fail(m, TF_ERR_INVALID, "tf_integrate_batch: empty item");
+    for (int f = 0; f < it.n_frames; f++) {
+      fr[f] = it.frames[f];
+      fr[f].flag = it.flag ? 1 : 0;
+    }
     if (it.flag == 0) {
-      // de-integration over kf.validChunks (GCFusion/MobileFusion.cpp:135-143): flags start true
-      upd.assign((size_t)it.n_ids, 1);
-      std::vector<tf_group_frame> fr(it.frames, it.frames + it.n_frames);
-      for (auto& f : fr) f.flag = 0;
-      if (int rc = tf_integrate_group(m, fr.data(), it.n_frames, cam, it.ids, it.n_ids, upd.data(), nullptr)) return rc;
-    } else {
-      std::vector<tf_group_frame> fr(it.frames, it.frames + it.n_frames);
-      for (auto& f : fr) f.flag = 1;
-      ids.resize(m->list_cap);
-      upd.resize(m->list_cap);
-      q.resize(m->list_cap);
-      tf_frame_stats st;
-      if (int rc = fused_group(m, fr.data(), it.n_frames, cam, &st, ids.data(), nullptr, upd.data(), q.data(), m->list_cap))
-        return rc;
-      int64_t nv = 0;
-      for (int64_t i = 0; i < st.n_chunks; i++) {
-        if (!upd[i]) continue;
-        if (nv < it.cap) {
-          if (it.valid_out) it.valid_out[nv] = ids[i];
-          if (it.quality_out) it.quality_out[nv] = q[i];
-        }
-        nv++;
+      // de-integration over kf.validChunks (GCFusion/MobileFusion.cpp:135-143); ids that are not in
+      // the map are skipped by the kernels and reported when the batch is flushed
+      if (it.n_ids == 0) continue;  // Structure/Chisel.h:228
+      GroupParams gp;
+      bool color[kMaxGroupFrames];
+      if (int rc = build_group(m, fr, it.n_frames, cam, gp, color)) return rc;
+      if (it.n_ids > m->list_cap) return fail(m, TF_ERR_CAPACITY, "chunk list exceeds the list capacity");
+      if (it.n_ids > kIdsStage - m->ids_stage_used) {  // staging full: drain what is queued
+        if (int rc = flush_batch(m, pend)) return rc;
+        CUDA_OK(m, cudaMemsetAsync(&m->fs->arena_off, 0, sizeof(int), m->stream));
       }
-      if (it.n_valid_out) *it.n_valid_out = nv;
-      if (nv > it.cap && it.valid_out) return fail(m, TF_ERR_CAPACITY, "tf_integrate_batch: valid_out too small");
+      const tf_chunk_id* src = it.ids;
+      if (it.n_ids <= kIdsStage) {
+        memcpy(m->ids_stage + m->ids_stage_used, it.ids, (size_t)it.n_ids * sizeof(int3));
+        src = reinterpret_cast<const tf_chunk_id*>(m->ids_stage + m->ids_stage_used);
+        m->ids_stage_used += it.n_ids;
+      }
+      if (int rc = upload_ids(m, src, it.n_ids)) return rc;
+      const int grid = (int)std::min<int64_t>(m->grid, (it.n_ids + kThreads - 1) / kThreads);
+      lookup_kernel<<<std::max(grid, 1), kThreads, 0, m->stream>>>(gp, m->md, m->fs, m->cb.list_ids, (int)it.n_ids,
+                                                                   m->cb.list_slots, m->cb.list_hpos, m->cb.list_setup);
+      if (int rc = check_kernel(m, "lookup_kernel")) return rc;
+      if (int rc = launch_integrate(m, gp, nullptr, (int)it.n_ids, algorithmic_bytes(m, it.n_ids, color, it.n_frames)))
+        return rc;
+      m->counters.frames_integrated += it.n_frames;
+      m->counters.voxel_updates += it.n_ids * 512 * it.n_frames;
+    } else {
+      FrameArgs a;
+      PendingItem p{};
+      p.it = &it;
+      p.rec = (int)pend.size();
+      p.n_frames = it.n_frames;
+      if (int rc = build_group(m, fr, it.n_frames, cam, a.gp, p.color)) return rc;
+      const int s = find_slot(m, fr[0].frame_index);
+      make_cull_params(m->cfg.voxel_res, m->cfg.trunc, fr[0].pose, *cam, a.cp);
+      a.depth = m->slots[s].depth;
+      a.want_order = 1;
+      a.any_color = false;
+      for (int f = 0; f < it.n_frames; f++) a.any_color |= p.color[f];
+      a.n_dev = &m->fs->n_work;
+      a.n_host = 0;
+      a.ff = FusedFinalize{};
+      a.ff.enabled = 1;
+      a.ff.ordered = 1;
+      a.ff.fs = m->fs;
+      a.ff.cb = m->cb;
+      a.ff.ids_out = m->st_ids;
+      a.ff.upd_out = m->st_upd;
+      a.ff.q_out = m->st_q;
+      a.ff.out_cap = m->list_cap;
+      a.ff.res = m->res_d;
+      a.ff.seq = ++m->seq;
+      a.ff.export_follows = 1;
+      a.want_export = true;
+      a.ex = ExportArgs{};
+      a.ex.ids_s = m->st_ids, a.ex.upd_s = m->st_upd, a.ex.q_s = m->st_q;
+      CUDA_OK(m, cudaHostGetDevicePointer((void**)&a.ex.ids_h, m->arena_ids, 0));
+      CUDA_OK(m, cudaHostGetDevicePointer((void**)&a.ex.upd_h, m->arena_upd, 0));
+      CUDA_OK(m, cudaHostGetDevicePointer((void**)&a.ex.q_h, m->arena_q, 0));
+      CUDA_OK(m, cudaHostGetDevicePointer((void**)&a.ex.batch_rec, m->batch_rec, 0));
+      a.ex.cap = m->list_cap;
+      a.ex.fs = m->fs;
+      a.ex.res = m->res_d;
+      a.ex.seq = a.ff.seq;
+      a.ex.batch_item = p.rec;
+      a.ex.arena_cap = kArenaCap;
+      m->parity ^= 1;
+      a.parity = m->parity;
+      p.first_event = m->ev_pending.size();
+      launch_frame_kernels(m, a, m->prof != 0);
+      p.n_events = m->ev_pending.size() - p.first_event;
+      if (int rc = check_kernel(m, "fused frame chain")) return rc;
+      m->counters.kernel_launches--;  // (check_kernel counted one launch too many)
+      pend.push_back(p);
+      if ((int)pend.size() == kSubBatch) {
+        if (int rc = flush_batch(m, pend)) return rc;
+        CUDA_OK(m, cudaMemsetAsync(&m->fs->arena_off, 0, sizeof(int), m->stream));
+      }
     }
   }
-  return TF_OK;
+  return flush_batch(m, pend);
 }
 
 #ifdef TF_TIMELINE
