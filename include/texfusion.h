@@ -179,7 +179,11 @@ int tf_integrate_frame(tf_map* m, int32_t frame_index, int use_color, const tf_p
  * ReIntegrateKeyframe call (:114-221).  flag 0: de-integrate the key-frame and its local
  * frames with their old poses over `ids` (= kf.validChunks).  flag 1: Prepare with the
  * key-frame's depth under its new pose, integrate the group, Finalize; the new valid list
- * is written to valid_out (cap entries) / *n_valid_out. */
+ * is written to valid_out (cap entries) / *n_valid_out.
+ * The items are applied in order but queued without intermediate host synchronisation (one per 32
+ * re-integrations); outputs are valid when the call returns.  Errors are therefore reported for
+ * the batch as a whole: a de-integration id that is not in the map is skipped and the call returns
+ * TF_ERR_NOT_FOUND after the remaining items have been applied. */
 typedef struct {
   int32_t flag;
   int32_t n_frames;               /* 1 key-frame + local frames */

@@ -464,3 +464,65 @@ def test_fused_frame_output_paths_agree(res):
     for name, m in variants.items():
         assert assert_maps_equal(m, o, what=name)
         m.close()
+
+
+def test_batch_is_order_preserving_across_sub_batches_and_reports_missing_ids():
+    """tf_integrate_batch queues its items without host synchronisation (one per 32
+    re-integrations): a long batch must give exactly the map and the valid lists of the same items
+    issued one call at a time, and a de-integration id that is not in the map is reported for the
+    batch as a whole."""
+    res = 0.02
+    from texturefusion_b200 import synth
+    cam = synth.Camera()
+    seq = synth.make_sequence(4, cam=cam, total=300, keyframe_every=2, with_drift=True, start=30)
+    groups = [seq.frames[0:2], seq.frames[2:4]]
+    a, b = capi.Map(res, max_frames=8), capi.Map(res, max_frames=8)
+    for m in (a, b):
+        for fr in seq.frames:
+            m.upload_frame(fr.index, fr.depth, fr.rgba() if fr.is_keyframe else None, fr.quality if fr.is_keyframe else None)
+
+    def item(group, flag, old, ids=None):
+        d = {"flag": flag, "frames": [(fr.index, k == 0, fr.pose_old if old else fr.pose) for k, fr in enumerate(group)]}
+        if ids is not None:
+            d["ids"] = ids
+        return d
+
+    first = [item(g, 1, True) for g in groups]
+    valid_a = [r[0] for r in a.integrate_batch(first, cam)]
+    valid_b = [b.integrate_batch([it], cam)[0][0] for it in first]
+    old = True
+    items, n_rounds = [], 18  # 18 x 2 key-frames = 36 re-integrations + 36 de-integrations: two sub-batches
+    # the batch needs every de-integration list up front, so build it from the one-at-a-time map first
+    seq_results = []
+    for r in range(n_rounds):
+        for k, g in enumerate(groups):
+            b.integrate_batch([item(g, 0, old, valid_b[k])], cam)
+            valid_b[k] = b.integrate_batch([item(g, 1, not old)], cam)[0][0]
+            seq_results.append(valid_b[k].copy())
+        old = not old
+    old = True
+    lists = [v.copy() for v in valid_a]
+    k_res = 0
+    for r in range(n_rounds):
+        for k, g in enumerate(groups):
+            items += [item(g, 0, old, lists[k]), item(g, 1, not old)]
+            lists[k] = seq_results[k_res]  # what the re-integration will return (checked below)
+            k_res += 1
+        old = not old
+    out = a.integrate_batch(items, cam)
+    got = [o[0] for o in out if o is not None]
+    assert len(got) == len(seq_results) == 36
+    for x, y in zip(got, seq_results):
+        assert np.array_equal(x, y)
+    ia, ib = sort_ids(a.list_chunks())[0], sort_ids(b.list_chunks())[0]
+    assert np.array_equal(ia, ib)
+    sa, sb = a.download_chunks(ia), b.download_chunks(ib)
+    for x, y in zip(sa, sb):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    # unknown id in a de-integration list
+    bad = np.vstack([lists[0][:3], np.array([[9999, 9999, 9999]], np.int32)])
+    with pytest.raises(capi.TexFusionError) as e:
+        a.integrate_batch([item(groups[0], 0, old, bad)], cam)
+    assert e.value.code == capi.TF_ERR_NOT_FOUND
+    a.close()
+    b.close()

@@ -347,11 +347,11 @@ int launch_integrate(tf_map* m, const GroupParams& gp, const int* n_dev, int n_h
   for (int f = 0; f < gp.n_frames; f++) any_color |= gp.f[f].rgba != nullptr;
   if (any_color)
     launch_pdl(integrate_kernel<true>, m->grid_integrate_c, integrate_smem_bytes(gp.n_frames), m->stream, gp, m->md,
-               (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, n_dev, n_host, &m->fs->work_next, m->list_upd,
+               (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, n_dev, n_host, m->list_upd,
                m->list_q, ff);
   else
     launch_pdl(integrate_kernel<false>, m->grid_integrate, integrate_smem_bytes(gp.n_frames), m->stream, gp, m->md,
-               (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, n_dev, n_host, &m->fs->work_next, m->list_upd,
+               (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, n_dev, n_host, m->list_upd,
                m->list_q, ff);
   if (m->prof) {
     prof_end(m, ep);
@@ -845,11 +845,11 @@ static void launch_frame_kernels(tf_map* m, FrameArgs& a, bool profile = false) 
   if (a.any_color)
     launch_pdl(integrate_kernel<true>, m->grid_integrate_c, integrate_smem_bytes(a.gp.n_frames), m->stream, a.gp, m->md,
                (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, a.n_dev,
-               a.n_host, &m->fs->work_next, m->list_upd, m->list_q, a.ff);
+               a.n_host, m->list_upd, m->list_q, a.ff);
   else
     launch_pdl(integrate_kernel<false>, m->grid_integrate, integrate_smem_bytes(a.gp.n_frames), m->stream, a.gp, m->md,
                (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, a.n_dev,
-               a.n_host, &m->fs->work_next, m->list_upd, m->list_q, a.ff);
+               a.n_host, m->list_upd, m->list_q, a.ff);
   if (profile) prof_end(m, ep);
   if (a.want_export) launch_pdl(export_kernel, export_grid(m), 0, m->stream, a.ex);
   m->counters.kernel_launches += a.want_export ? 4 : 3;
@@ -902,11 +902,10 @@ static int launch_frame_graph(tf_map* m, FrameGraph& fg, FrameArgs& a) {
   const int* list_slots = m->cb.list_slots;
   const int* list_hpos = m->cb.list_hpos;
   const float* list_setup = m->cb.list_setup;
-  int* work_next = &m->fs->work_next;
   void* p_bbox[] = {&a.cp, &a.depth, &m->fs, &a.parity};
   void* p_cull[] = {&a.cp, &a.gp, &m->md, &a.depth, &m->fs, &m->cb, &m->cfg.n_ranks, &m->cfg.rank, &a.parity, &a.want_order};
-  void* p_int[] = {&a.gp, &m->md, &list_slots, &list_hpos, &list_setup, &a.n_dev, &a.n_host, &work_next, &m->list_upd,
-                   &m->list_q, &a.ff};
+  void* p_int[] = {&a.gp, &m->md, &list_slots, &list_hpos, &list_setup, &a.n_dev, &a.n_host, &m->list_upd, &m->list_q,
+                   &a.ff};
   void* p_exp[] = {&a.ex};
   void** params[4] = {p_bbox, p_cull, p_int, p_exp};
   const int n_nodes = a.want_export ? 4 : 3;
