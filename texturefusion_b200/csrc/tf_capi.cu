@@ -926,18 +926,19 @@ static int launch_frame_graph(tf_map* m, FrameGraph& fg, FrameArgs& a) {
 // memory).  Polling it returns a few microseconds earlier than cudaStreamSynchronize; the stream
 // is queried now and then so that a failed kernel cannot hang the caller.
 static int wait_frame(tf_map* m, unsigned seq) {
-  volatile unsigned* p = &m->res_h->seq;
-  for (unsigned it = 1; *p != seq; it++) {
+  volatile FrameResultHost* r = m->res_h;
+  auto done = [&] { return r->seq == seq && r->seq0 == seq && r->seq1 == seq; };
+  for (unsigned it = 1; !done(); it++) {
     if ((it & 0x3fffu) == 0) {
       const cudaError_t e = cudaStreamQuery(m->stream);
-      if (e == cudaSuccess) break;  // finished: the stamp is there (or the kernels did not publish)
+      if (e == cudaSuccess) break;  // finished: the stamps are there (or the kernels did not publish)
       if (e != cudaErrorNotReady) return fail(m, TF_ERR_CUDA, std::string("fused frame: ") + cudaGetErrorString(e));
     }
   }
   std::atomic_thread_fence(std::memory_order_acquire);
-  if (*p != seq) {  // stream idle without a stamp: surface whatever went wrong
+  if (!done()) {  // stream idle without a stamp: surface whatever went wrong
     CUDA_OK(m, cudaStreamSynchronize(m->stream));
-    if (*p != seq) return fail(m, TF_ERR_CUDA, "fused frame: kernels finished without publishing a result");
+    if (!done()) return fail(m, TF_ERR_CUDA, "fused frame: kernels finished without publishing a result");
   }
   return TF_OK;
 }
