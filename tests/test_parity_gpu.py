@@ -526,3 +526,27 @@ def test_batch_is_order_preserving_across_sub_batches_and_reports_missing_ids():
     assert e.value.code == capi.TF_ERR_NOT_FOUND
     a.close()
     b.close()
+
+
+def test_batch_items_without_outputs_stream_a_sequence():
+    """Single-frame re-integration items that ask for nothing back (no valid list) queue a frame
+    sequence without host round trips; the map must equal the one built frame by frame."""
+    res = 0.02
+    seq = room_sequence(8)
+    cam = seq.cam
+    a, b = capi.Map(res, max_frames=16), capi.Map(res, max_frames=16)
+    for m in (a, b):
+        for fr in seq.frames:
+            m.upload_frame(fr.index, fr.depth, fr.rgba() if fr.is_keyframe else None, fr.quality if fr.is_keyframe else None)
+    items = [{"flag": 1, "frames": [(fr.index, fr.is_keyframe, fr.pose)]} for fr in seq.frames]
+    out = a.run_batch(a.marshal_batch(items, want_lists=False), cam)
+    assert all(o is None for o in out)
+    for fr in seq.frames:
+        b.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam, want_lists=False)
+    ia, ib = sort_ids(a.list_chunks())[0], sort_ids(b.list_chunks())[0]
+    assert np.array_equal(ia, ib) and len(ia) > 0
+    for x, y in zip(a.download_chunks(ia), b.download_chunks(ib)):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    assert a.counters()["voxel_updates"] == b.counters()["voxel_updates"]
+    a.close()
+    b.close()

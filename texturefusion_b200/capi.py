@@ -299,9 +299,10 @@ class Map:
             return st, ids[:n].copy(), new[:n].copy(), upd[:n].copy(), q[:n].copy()
         return st, None, None, None, None
 
-    def marshal_batch(self, items, cap=None):
+    def marshal_batch(self, items, cap=None, want_lists=True):
         """Builds the tf_batch_item array of integrate_batch (kept separate so that a benchmark can
-        time the C call alone).  Returns an opaque tuple for run_batch."""
+        time the C call alone).  Returns an opaque tuple for run_batch.  want_lists=False: the
+        re-integration items ask for nothing back (streaming fusion of a frame sequence)."""
         cap = cap or self.list_cap
         n = len(items)
         arr = (BatchItem * n)()
@@ -319,6 +320,8 @@ class Map:
                 keep.append(ids)
                 arr[k].ids = ids.ctypes.data
                 arr[k].n_ids = len(ids)
+                outs.append(None)
+            elif not want_lists:
                 outs.append(None)
             else:
                 valid = np.empty((cap, 3), np.int32)

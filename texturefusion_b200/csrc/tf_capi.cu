@@ -95,7 +95,7 @@ struct tf_map {
   int3* arena_ids = nullptr;
   float* arena_q = nullptr;
   unsigned char* arena_upd = nullptr;
-  int2* batch_rec = nullptr;
+  int4* batch_rec = nullptr;
   int3* ids_stage = nullptr;     // page-locked staging of the de-integration lists (pageable sources would
   int64_t ids_stage_used = 0;    // make cudaMemcpyAsync wait for the stream, i.e. serialise host and device)
   int3* st_ids = nullptr;  // device staging of the ordered per-chunk outputs (export_kernel)
@@ -1064,13 +1064,16 @@ constexpr int kArenaCap = 1 << 22;     // list entries per sub-batch
 constexpr int kSubBatch = 32;          // re-integration items per synchronisation
 constexpr int64_t kIdsStage = 1 << 20; // staged de-integration ids per synchronisation
 
-static int ensure_arena(tf_map* m) {
-  if (m->arena_ids) return TF_OK;
-  CUDA_OK(m, cudaHostAlloc((void**)&m->arena_ids, (size_t)kArenaCap * sizeof(int3), cudaHostAllocMapped));
-  CUDA_OK(m, cudaHostAlloc((void**)&m->arena_q, (size_t)kArenaCap * sizeof(float), cudaHostAllocMapped));
-  CUDA_OK(m, cudaHostAlloc((void**)&m->arena_upd, (size_t)kArenaCap, cudaHostAllocMapped));
-  CUDA_OK(m, cudaHostAlloc((void**)&m->batch_rec, (size_t)kSubBatch * sizeof(int2), cudaHostAllocMapped));
-  CUDA_OK(m, cudaHostAlloc((void**)&m->ids_stage, (size_t)kIdsStage * sizeof(int3), cudaHostAllocDefault));
+// (page-locking tens of megabytes takes tens of milliseconds: only what a batch needs, once)
+static int ensure_arena(tf_map* m, bool lists, bool ids) {
+  if (!m->batch_rec) CUDA_OK(m, cudaHostAlloc((void**)&m->batch_rec, (size_t)kSubBatch * sizeof(int4), cudaHostAllocMapped));
+  if (lists && !m->arena_ids) {
+    CUDA_OK(m, cudaHostAlloc((void**)&m->arena_ids, (size_t)kArenaCap * sizeof(int3), cudaHostAllocMapped));
+    CUDA_OK(m, cudaHostAlloc((void**)&m->arena_q, (size_t)kArenaCap * sizeof(float), cudaHostAllocMapped));
+    CUDA_OK(m, cudaHostAlloc((void**)&m->arena_upd, (size_t)kArenaCap, cudaHostAllocMapped));
+  }
+  if (ids && !m->ids_stage)
+    CUDA_OK(m, cudaHostAlloc((void**)&m->ids_stage, (size_t)kIdsStage * sizeof(int3), cudaHostAllocDefault));
   return TF_OK;
 }
 
@@ -1091,7 +1094,7 @@ static int flush_batch(tf_map* m, std::vector<PendingItem>& pend) {
   const int dev_err = m->res_h->error;
   int rc = TF_OK;
   for (const PendingItem& p : pend) {
-    const int2 r = m->batch_rec[p.rec];
+    const int4 r = m->batch_rec[p.rec];
     if (r.x < 0) { rc = fail(m, TF_ERR_CAPACITY, "tf_integrate_batch: result arena exhausted"); continue; }
     const int3* ids = m->arena_ids + r.y;
     const float* q = m->arena_q + r.y;
@@ -1107,11 +1110,11 @@ static int flush_batch(tf_map* m, std::vector<PendingItem>& pend) {
     }
     if (p.it->n_valid_out) *p.it->n_valid_out = nv;
     if (nv > p.it->cap && p.it->valid_out) rc = fail(m, TF_ERR_CAPACITY, "tf_integrate_batch: valid_out too small");
-    m->counters.d2h_bytes += (int64_t)r.x * 17;
+    m->counters.d2h_bytes += (int64_t)r.x * 17 + sizeof(int4);
     m->counters.frames_integrated += p.n_frames;
-    m->counters.voxel_updates += (int64_t)r.x * 512 * p.n_frames;
+    m->counters.voxel_updates += (int64_t)r.z * 512 * p.n_frames;
     for (size_t e = p.first_event; e < p.first_event + p.n_events && e < m->ev_pending.size(); e++)
-      m->ev_pending[e].bytes = algorithmic_bytes(m, r.x, p.color, p.n_frames);
+      m->ev_pending[e].bytes = algorithmic_bytes(m, r.z, p.color, p.n_frames);
   }
   pend.clear();
   m->ids_stage_used = 0;
@@ -1124,14 +1127,17 @@ int tf_integrate_batch(tf_map* m, const tf_batch_item* items, int64_t n_items, c
   if (!m || n_items < 0 || (n_items > 0 && !items) || !cam_ok(m, cam))
     return fail(m, TF_ERR_INVALID, "tf_integrate_batch: bad argument");
   int max_frames = 1;
+  bool any_lists = false, any_ids = false;
   for (int64_t k = 0; k < n_items; k++) {
+    if (items[k].flag == 0) any_ids = true;
+    else if (items[k].valid_out || items[k].quality_out || items[k].n_valid_out) any_lists = true;
     if (!items[k].frames || items[k].n_frames < 1 || items[k].n_frames > kMaxGroupFrames)
       return fail(m, TF_ERR_INVALID, "tf_integrate_batch: group size must be 1..8");
     if (items[k].flag == 0 && (items[k].n_ids < 0 || (items[k].n_ids > 0 && !items[k].ids)))
       return fail(m, TF_ERR_INVALID, "tf_integrate_batch: de-integration item without a chunk list");
     max_frames = std::max(max_frames, items[k].n_frames);
   }
-  if (int rc = ensure_arena(m)) return rc;
+  if (int rc = ensure_arena(m, any_lists, any_ids)) return rc;
   if (int rc = ensure_setup(m, max_frames)) return rc;
   CUDA_OK(m, cudaMemsetAsync(&m->fs->arena_off, 0, sizeof(int), m->stream));
   std::vector<PendingItem> pend;
@@ -1178,32 +1184,37 @@ int tf_integrate_batch(tf_map* m, const tf_batch_item* items, int64_t n_items, c
       if (int rc = build_group(m, fr, it.n_frames, cam, a.gp, p.color)) return rc;
       const int s = find_slot(m, fr[0].frame_index);
       make_cull_params(m->cfg.voxel_res, m->cfg.trunc, fr[0].pose, *cam, a.cp);
+      // (an item that asks for nothing back — streaming fusion of a frame sequence — skips the
+      //  ordering scan and the export; only its list length is recorded)
+      const bool want_lists = it.valid_out || it.quality_out || it.n_valid_out;
       a.depth = m->slots[s].depth;
-      a.want_order = 1;
+      a.want_order = want_lists ? 1 : 0;
       a.any_color = false;
       for (int f = 0; f < it.n_frames; f++) a.any_color |= p.color[f];
       a.n_dev = &m->fs->n_work;
       a.n_host = 0;
       a.ff = FusedFinalize{};
       a.ff.enabled = 1;
-      a.ff.ordered = 1;
+      a.ff.ordered = want_lists ? 1 : 0;
       a.ff.fs = m->fs;
       a.ff.cb = m->cb;
-      a.ff.ids_out = m->st_ids;
-      a.ff.upd_out = m->st_upd;
-      a.ff.q_out = m->st_q;
+      a.ff.ids_out = want_lists ? m->st_ids : nullptr;
+      a.ff.upd_out = want_lists ? m->st_upd : nullptr;
+      a.ff.q_out = want_lists ? m->st_q : nullptr;
       a.ff.out_cap = m->list_cap;
       a.ff.res = m->res_d;
       a.ff.seq = ++m->seq;
       a.ff.export_follows = 1;
-      a.want_export = true;
+      a.want_export = true;  // (without lists the export kernel only records the item's list length)
       a.ex = ExportArgs{};
-      a.ex.ids_s = m->st_ids, a.ex.upd_s = m->st_upd, a.ex.q_s = m->st_q;
-      CUDA_OK(m, cudaHostGetDevicePointer((void**)&a.ex.ids_h, m->arena_ids, 0));
-      CUDA_OK(m, cudaHostGetDevicePointer((void**)&a.ex.upd_h, m->arena_upd, 0));
-      CUDA_OK(m, cudaHostGetDevicePointer((void**)&a.ex.q_h, m->arena_q, 0));
+      if (want_lists) {
+        a.ex.ids_s = m->st_ids, a.ex.upd_s = m->st_upd, a.ex.q_s = m->st_q;
+        CUDA_OK(m, cudaHostGetDevicePointer((void**)&a.ex.ids_h, m->arena_ids, 0));
+        CUDA_OK(m, cudaHostGetDevicePointer((void**)&a.ex.upd_h, m->arena_upd, 0));
+        CUDA_OK(m, cudaHostGetDevicePointer((void**)&a.ex.q_h, m->arena_q, 0));
+      }
       CUDA_OK(m, cudaHostGetDevicePointer((void**)&a.ex.batch_rec, m->batch_rec, 0));
-      a.ex.cap = m->list_cap;
+      a.ex.cap = want_lists ? m->list_cap : 0;
       a.ex.fs = m->fs;
       a.ex.res = m->res_d;
       a.ex.seq = a.ff.seq;
