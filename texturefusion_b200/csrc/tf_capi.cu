@@ -70,6 +70,7 @@ struct tf_map {
   std::string err;
   float* slab_depth = nullptr;          // frame store: depth planes of all slots
   unsigned char* slab_color = nullptr;  // rgba | quality | rgb | valid planes of all slots
+  int grid_bbox = 0;
   int sm_count = 0, grid = 0, grid_cull = 0, grid_integrate = 0, grid_integrate_c = 0;
 
   MapDev md{};
@@ -322,7 +323,7 @@ int launch_cull(tf_map* m, const CullParams& cp, const GroupParams& gp, const fl
   if (st) prof_begin(m, ep);
   m->parity ^= 1;
   HT(2);
-  bbox_kernel<<<m->grid, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->parity);
+  bbox_kernel<<<m->grid_bbox, kThreads, 0, m->stream>>>(cp, depth, m->fs, m->parity);
   HT(3);
   if (st) { prof_end(m, ep, 0); prof_begin(m, ep); }
   if (int rc = check_kernel(m, "bbox_kernel")) return rc;
@@ -543,6 +544,7 @@ int tf_create(tf_map** out, const tf_config* cfg) {
   C_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, integrate_kernel<true>, kThreads, integrate_smem_bytes(1)));
   m->grid_integrate_c = m->sm_count * std::max(1, occ_c);
   m->grid = m->sm_count * 2;
+  m->grid_bbox = std::max(m->grid, (m->npix / 4 + kThreads - 1) / kThreads);  // one float4 per thread
   m->grid_cull = m->sm_count * 4;
   m->grid_integrate = m->sm_count * std::max(1, occ);
 
@@ -604,9 +606,10 @@ int tf_create(tf_map** out, const tf_config* cfg) {
   // The frame store is allocated up front as two slabs (16 B per pixel and slot with colour):
   // cudaMalloc in the per-frame path would stall the stream for hundreds of microseconds.
   m->slots.resize(max_frames);
-  C_OK(dmalloc(&m->slab_depth, (size_t)m->npix * max_frames));
+  const size_t depth_stride = ((size_t)m->npix + 3) & ~(size_t)3;  // keeps every plane 16-byte aligned (float4 loads)
+  C_OK(dmalloc(&m->slab_depth, depth_stride * max_frames));
   for (int i = 0; i < max_frames; i++) {
-    m->slots[i].depth = m->slab_depth + (size_t)i * m->npix;
+    m->slots[i].depth = m->slab_depth + (size_t)i * depth_stride;
     C_OK(cudaEventCreateWithFlags(&m->slots[i].ready, cudaEventDisableTiming));
   }
   if (cfg->use_color) {
@@ -837,7 +840,7 @@ static int export_grid(const tf_map* m) {
 }
 
 static void launch_frame_kernels(tf_map* m, FrameArgs& a, bool profile = false) {
-  bbox_kernel<<<m->grid, kThreads, 0, m->stream>>>(a.cp, a.depth, m->fs, a.parity);
+  bbox_kernel<<<m->grid_bbox, kThreads, 0, m->stream>>>(a.cp, a.depth, m->fs, a.parity);
   launch_pdl(cull_kernel<true>, m->grid_cull, 0, m->stream, a.cp, a.gp, m->md, a.depth, m->fs, m->cb, m->cfg.n_ranks,
              m->cfg.rank, a.parity, a.want_order);
   EventPair ep;
