@@ -444,6 +444,9 @@ def test_fused_frame_output_paths_agree(res):
         for name, m in variants.items():
             if i + 1 < len(frames):
                 upload(m, frames[i + 1])  # in flight during this frame's kernels
+                if name == "graph+pinned":
+                    assert m.L.tf_wait_upload(m.h, frames[i + 1].index) == 0
+                    assert m.L.tf_wait_upload(m.h, 987654) == capi.TF_ERR_NOT_FOUND
             if name == "graph+pinned":
                 st = capi.FrameStats()
                 rc = m.L.tf_integrate_frame(m.h, fr.index, int(fr.is_keyframe), C.byref(capi.make_pose(fr.pose)),

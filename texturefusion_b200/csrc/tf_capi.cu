@@ -347,7 +347,7 @@ int launch_integrate(tf_map* m, const GroupParams& gp, const int* n_dev, int n_h
   bool any_color = false;
   for (int f = 0; f < gp.n_frames; f++) any_color |= gp.f[f].rgba != nullptr;
   if (any_color)
-    launch_pdl(integrate_kernel<true>, m->grid_integrate_c, integrate_smem_bytes(gp.n_frames), m->stream, gp, m->md,
+    launch_pdl(integrate_kernel<true>, m->grid_integrate_c, integrate_smem_bytes(gp.n_frames, true), m->stream, gp, m->md,
                (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, n_dev, n_host, m->list_upd,
                m->list_q, ff);
   else
@@ -538,10 +538,10 @@ int tf_create(tf_map** out, const tf_config* cfg) {
   C_OK(cudaFuncSetAttribute(integrate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)integrate_smem_bytes(kMaxGroupFrames)));
   C_OK(cudaFuncSetAttribute(integrate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)integrate_smem_bytes(kMaxGroupFrames)));
+                            (int)std::max(integrate_smem_bytes(kMaxGroupFrames, true), integrate_smem_bytes(1, true))));
   int occ_c = 1;
   C_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, integrate_kernel<false>, kThreads, integrate_smem_bytes(1)));
-  C_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, integrate_kernel<true>, kThreads, integrate_smem_bytes(1)));
+  C_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, integrate_kernel<true>, kThreads, integrate_smem_bytes(1, true)));
   m->grid_integrate_c = m->sm_count * std::max(1, occ_c);
   m->grid = m->sm_count * 2;
   m->grid_bbox = std::max(m->grid, (m->npix / 4 + kThreads - 1) / kThreads);  // one float4 per thread
@@ -846,7 +846,7 @@ static void launch_frame_kernels(tf_map* m, FrameArgs& a, bool profile = false) 
   EventPair ep;
   if (profile) prof_begin(m, ep);
   if (a.any_color)
-    launch_pdl(integrate_kernel<true>, m->grid_integrate_c, integrate_smem_bytes(a.gp.n_frames), m->stream, a.gp, m->md,
+    launch_pdl(integrate_kernel<true>, m->grid_integrate_c, integrate_smem_bytes(a.gp.n_frames, true), m->stream, a.gp, m->md,
                (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, a.n_dev,
                a.n_host, m->list_upd, m->list_q, a.ff);
   else
