@@ -553,3 +553,78 @@ def test_batch_items_without_outputs_stream_a_sequence():
     assert a.counters()["voxel_updates"] == b.counters()["voxel_updates"]
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("seed", (0, 1, 2))
+def test_random_protocol_mix_matches_oracle(seed):
+    """State-machine fuzz: one map driven by a random mix of the entry points — fused frames with and
+    without lists, the split Prepare / Integrate / Finalize protocol, queued batches and
+    de-/re-integration of earlier key-frames, with tf_reset in between — must stay bit-identical to
+    the oracle driven by the same calls (allocator, free stack, lazy chunks, garbage collection and
+    the frame store are shared by all of these paths)."""
+    rng = np.random.RandomState(seed)
+    res = (0.02, 0.01, 0.005)[seed]
+    from texturefusion_b200 import synth
+    cam = synth.Camera()
+    seq = synth.make_sequence(12, cam=cam, total=300, keyframe_every=3, with_drift=True, start=90 + 21 * seed)
+    groups = [seq.frames[k:k + 3] for k in range(0, 12, 3)]
+    g = capi.Map(res, max_frames=16)
+    o = OracleMap(res)
+    for fr in seq.frames:
+        g.upload_frame(fr.index, fr.depth, fr.rgba() if fr.is_keyframe else None, fr.quality if fr.is_keyframe else None)
+    fused_in = {}  # key-frame group index -> (poses used, valid list) for groups currently in the map
+
+    def item(group, flag, poses, ids=None):
+        d = {"flag": flag, "frames": [(fr.index, k == 0, poses[k]) for k, fr in enumerate(group)]}
+        if ids is not None:
+            d["ids"] = ids
+        return d
+
+    for step in range(14):
+        free = [k for k in range(len(groups)) if k not in fused_in]
+        op = rng.choice(["fused", "fused_nolists", "split", "batch_in", "batch_out", "reset"],
+                        p=[0.2, 0.15, 0.15, 0.25, 0.2, 0.05])
+        if op in ("fused", "fused_nolists"):
+            fr = seq.frames[rng.randint(len(seq.frames))]
+            rgba = fr.rgba() if fr.is_keyframe else None
+            st, ids, new, upd, q = g.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam, want_lists=(op == "fused"))
+            oi, onew = o.prepare(fr.depth, fr.pose, cam)
+            onu, _ = o.integrate(fr.depth, rgba, fr.quality if fr.is_keyframe else None, fr.pose, cam, oi, 1, -1)
+            o.finalize(oi, onu, onew)
+            assert st.n_chunks == len(oi) and st.n_updated == int(np.count_nonzero(onu))
+            if op == "fused":
+                assert np.array_equal(ids, oi) and np.array_equal(upd != 0, np.asarray(onu) != 0)
+        elif op == "split":
+            fr = seq.frames[rng.randint(len(seq.frames))]
+            ids, new = g.prepare(fr.index, fr.pose, cam)
+            oi, onew = o.prepare(fr.depth, fr.pose, cam)
+            assert np.array_equal(ids, oi) and np.array_equal(new, onew)
+            nu, _ = g.integrate(fr.index, False, fr.pose, cam, ids, 1)
+            onu, _ = o.integrate(fr.depth, None, None, fr.pose, cam, oi, 1, -1)
+            assert np.array_equal(nu != 0, np.asarray(onu) != 0)
+            garbage = ids[(nu == 0) & (new != 0)]
+            if len(garbage):
+                g.remove_chunks(garbage)
+            o.finalize(oi, onu, onew)
+        elif op == "batch_in" and free:
+            ks = [int(k) for k in rng.choice(free, size=min(len(free), 1 + rng.randint(2)), replace=False)]
+            old = bool(rng.randint(2))
+            poses = {k: [fr.pose_old if old else fr.pose for fr in groups[k]] for k in ks}
+            out = g.integrate_batch([item(groups[k], 1, poses[k]) for k in ks], cam)
+            for k, (gv, gq) in zip(ks, out):
+                ov, oq = _oracle_keyframe_group(o, cam, groups[k], poses[k], 1)
+                assert np.array_equal(gv, ov) and np.array_equal(gq.view(np.uint32), oq.view(np.uint32))
+                fused_in[k] = (poses[k], ov)
+        elif op == "batch_out" and fused_in:
+            k = int(rng.choice(list(fused_in)))
+            poses, vl = fused_in.pop(k)
+            if len(vl):
+                g.integrate_batch([item(groups[k], 0, poses, vl)], cam)
+                _oracle_keyframe_group(o, cam, groups[k], poses, 0, vl)
+        elif op == "reset":
+            g.reset()
+            o.reset()
+            fused_in.clear()
+        assert g.chunk_count() == o.chunk_count(), f"step {step} ({op})"
+    assert assert_maps_equal(g, o, what=f"protocol mix seed {seed}")
+    g.close()
