@@ -628,3 +628,27 @@ def test_random_protocol_mix_matches_oracle(seed):
         assert g.chunk_count() == o.chunk_count(), f"step {step} ({op})"
     assert assert_maps_equal(g, o, what=f"protocol mix seed {seed}")
     g.close()
+
+
+@pytest.mark.parametrize("scale,res", ((0.35, 0.02), (0.1, 0.04), (1.7, 0.01)))
+def test_other_image_sizes(scale, res):
+    """Images other than 640x480 (224x168, 64x48, 1088x816; the width must stay a multiple of 8 like
+    the reference's 8-pixel loops): plane strides in the frame-store slabs, grid sizes derived from
+    the pixel count, and a principal point that changes the rounding slack of the projection."""
+    seq = room_sequence(4, scale=scale)
+    cam = seq.cam
+    assert cam.width % 8 == 0
+    with pytest.raises(capi.TexFusionError):
+        capi.Map(res, width=cam.width + 3, height=cam.height)
+    g = capi.Map(res, width=cam.width, height=cam.height, max_frames=8)
+    o = OracleMap(res)
+    for fr in seq.frames:
+        rgba = fr.rgba() if fr.is_keyframe else None
+        g.upload_frame(fr.index, fr.depth, rgba, fr.quality if fr.is_keyframe else None)
+        st, ids, new, upd, q = g.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam)
+        oi, onew = o.prepare(fr.depth, fr.pose, cam)
+        onu, _ = o.integrate(fr.depth, rgba, fr.quality if fr.is_keyframe else None, fr.pose, cam, oi, 1, -1)
+        o.finalize(oi, onu, onew)
+        assert np.array_equal(ids, oi) and np.array_equal(upd != 0, np.asarray(onu) != 0)
+    assert assert_maps_equal(g, o, what=f"image {cam.width}x{cam.height}")
+    g.close()
