@@ -140,8 +140,8 @@ int tf_integrate(tf_map* m, int32_t frame_index, int use_color, const tf_pose* p
                  const tf_camera* cam, const tf_chunk_id* ids, int64_t n, int flag,
                  uint8_t* needs_update_inout, float* quality_out_or_null);
 
-/* One group of frames applied, in order, to ONE chunk list with the voxels held in
- * registers (a key-frame followed by its local depth frames,
+/* One group of frames applied, in order, to ONE chunk list with each chunk's voxels held on
+ * chip across the group (a key-frame followed by its local depth frames,
  * GCFusion/MobileFusion.cpp:176-203).  Same result as n_frames tf_integrate calls. */
 typedef struct {
   int32_t frame_index;
@@ -183,7 +183,9 @@ int tf_integrate_frame(tf_map* m, int32_t frame_index, int use_color, const tf_p
  * The items are applied in order but queued without intermediate host synchronisation (one per 32
  * re-integrations); outputs are valid when the call returns.  Errors are therefore reported for
  * the batch as a whole: a de-integration id that is not in the map is skipped and the call returns
- * TF_ERR_NOT_FOUND after the remaining items have been applied. */
+ * TF_ERR_NOT_FOUND after the remaining items have been applied.  A flag-1 item whose three output
+ * pointers are all NULL only fuses its frames (a sequence of such single-frame items streams a
+ * recording into the map without a host round trip per frame). */
 typedef struct {
   int32_t flag;
   int32_t n_frames;               /* 1 key-frame + local frames */
