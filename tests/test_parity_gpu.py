@@ -652,3 +652,28 @@ def test_other_image_sizes(scale, res):
         assert np.array_equal(ids, oi) and np.array_equal(upd != 0, np.asarray(onu) != 0)
     assert assert_maps_equal(g, o, what=f"image {cam.width}x{cam.height}")
     g.close()
+
+
+def test_colour_count_overflow_shift():
+    """ProjectionIntegrator.cpp:274-292: once a voxel's colour count exceeds 120 all four u16
+    accumulators are shifted right by two.  130 integrations of the same key-frame drive every
+    observed voxel through that branch (and 130 de-integrations through the wrapping subtract)."""
+    res = 0.04
+    seq = room_sequence(1, keyframe_every=1, scale=0.25)
+    cam, fr = seq.cam, seq.frames[0]
+    g = capi.Map(res, width=cam.width, height=cam.height, max_frames=4)
+    o = OracleMap(res)
+    g.upload_frame(fr.index, fr.depth, fr.rgba(), fr.quality)
+    for _ in range(130):
+        g.integrate_frame(fr.index, True, fr.pose, cam, want_lists=False)
+        o.integrate_frame(fr.depth, fr.rgba(), fr.quality, fr.pose, cam, -1)
+    ids = sort_ids(g.list_chunks())[0]
+    _, _, col = g.download_chunks(ids)
+    counts = col.reshape(len(ids), 512, 4)[:, :, 3]
+    assert counts.max() <= 120 + 1 and (counts > 30).any(), "the shift branch was not reached"
+    assert assert_maps_equal(g, o, what="130 colour integrations")
+    for _ in range(3):  # wrapping de-integration of shifted accumulators, over every chunk of the map
+        g.integrate(fr.index, True, fr.pose, cam, ids, 0)
+        o.integrate(fr.depth, fr.rgba(), fr.quality, fr.pose, cam, ids, 0, -1)
+    assert assert_maps_equal(g, o, what="de-integration after the shift")
+    g.close()
