@@ -677,3 +677,26 @@ def test_colour_count_overflow_shift():
         o.integrate(fr.depth, fr.rgba(), fr.quality, fr.pose, cam, ids, 0, -1)
     assert assert_maps_equal(g, o, what="de-integration after the shift")
     g.close()
+
+
+@pytest.mark.parametrize("res", (0.02, 0.005))
+def test_near_and_far_planes_inside_the_depth_range(res):
+    """Depth values outside (near, far) of the camera handed to the fusion call: the culling gates
+    (block origin depth, ChunkManager.h:598-602) and the TSDF gate (ProjectionIntegrator.cpp:310-317)
+    must cut exactly where the reference cuts."""
+    import dataclasses
+    seq = room_sequence(3)
+    cam = dataclasses.replace(seq.cam, near=0.9, far=2.2)
+    g = capi.Map(res)
+    o = OracleMap(res)
+    for fr in seq.frames:
+        rgba = fr.rgba() if fr.is_keyframe else None
+        g.upload_frame(fr.index, fr.depth, rgba, fr.quality if fr.is_keyframe else None)
+        st, ids, new, upd, q = g.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam)
+        oi, onew = o.prepare(fr.depth, fr.pose, cam)
+        onu, _ = o.integrate(fr.depth, rgba, fr.quality if fr.is_keyframe else None, fr.pose, cam, oi, 1, -1)
+        o.finalize(oi, onu, onew)
+        assert np.array_equal(ids, oi) and np.array_equal(upd != 0, np.asarray(onu) != 0)
+        assert 0 < int(np.count_nonzero(onu)) < len(oi)
+    assert assert_maps_equal(g, o, what="near/far inside the depth range")
+    g.close()
