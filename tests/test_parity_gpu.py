@@ -700,3 +700,30 @@ def test_near_and_far_planes_inside_the_depth_range(res):
         assert 0 < int(np.count_nonzero(onu)) < len(oi)
     assert assert_maps_equal(g, o, what="near/far inside the depth range")
     g.close()
+
+
+def test_noisy_depth_sequence_bit_exact():
+    """Gaussian depth noise (sigma 2 mm) makes pixel roundings, band edges and the early-exit rows
+    irregular; fused frames and a three-frame group against the oracle at 5 mm."""
+    res = 0.005
+    seq = room_sequence(6, noise=0.002, start=123)
+    cam = seq.cam
+    g = capi.Map(res)
+    o = OracleMap(res)
+    for fr in seq.frames[:3]:
+        rgba = fr.rgba() if fr.is_keyframe else None
+        g.upload_frame(fr.index, fr.depth, rgba, fr.quality if fr.is_keyframe else None)
+        st, ids, new, upd, q = g.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam)
+        oi, onew = o.prepare(fr.depth, fr.pose, cam)
+        onu, _ = o.integrate(fr.depth, rgba, fr.quality if fr.is_keyframe else None, fr.pose, cam, oi, 1, -1)
+        o.finalize(oi, onu, onew)
+        assert np.array_equal(ids, oi) and np.array_equal(upd != 0, np.asarray(onu) != 0)
+    group = seq.frames[3:6]
+    for fr in group:
+        g.upload_frame(fr.index, fr.depth, fr.rgba() if fr.is_keyframe else None, fr.quality if fr.is_keyframe else None)
+    assert group[0].is_keyframe
+    out = g.integrate_batch([{"flag": 1, "frames": [(fr.index, k == 0, fr.pose) for k, fr in enumerate(group)]}], cam)
+    ov, oq = _oracle_keyframe_group(o, cam, group, [fr.pose for fr in group], 1)
+    assert np.array_equal(out[0][0], ov) and np.array_equal(out[0][1].view(np.uint32), oq.view(np.uint32))
+    assert assert_maps_equal(g, o, what="noisy depth")
+    g.close()
