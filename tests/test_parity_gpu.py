@@ -727,3 +727,27 @@ def test_noisy_depth_sequence_bit_exact():
     assert np.array_equal(out[0][0], ov) and np.array_equal(out[0][1].view(np.uint32), oq.view(np.uint32))
     assert assert_maps_equal(g, o, what="noisy depth")
     g.close()
+
+
+def test_maps_on_two_devices_in_one_process():
+    """Every entry point selects its map's device: two maps on different GPUs driven alternately from
+    one thread (whatever the thread's current device is) must both match the oracle."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    res = 0.02
+    seq = room_sequence(4)
+    cam = seq.cam
+    maps = [capi.Map(res, device=0), capi.Map(res, device=1)]
+    o = OracleMap(res)
+    for fr in seq.frames:
+        rgba = fr.rgba() if fr.is_keyframe else None
+        o.integrate_frame(fr.depth, rgba, fr.quality, fr.pose, cam, -1)
+        for k, m in enumerate(maps):
+            torch.cuda.set_device(1 - k)  # deliberately the other one
+            m.upload_frame(fr.index, fr.depth, rgba, fr.quality if fr.is_keyframe else None)
+            m.integrate_frame(fr.index, fr.is_keyframe, fr.pose, cam)
+    torch.cuda.set_device(0)
+    for k, m in enumerate(maps):
+        assert assert_maps_equal(m, o, what=f"map on device {k}")
+        m.close()

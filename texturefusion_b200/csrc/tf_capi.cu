@@ -202,6 +202,13 @@ int check_kernel(tf_map* m, const char* what) {
   return TF_OK;
 }
 
+// Every entry point that touches the device first makes the map's device current: a process may
+// hold maps on several GPUs (or another library may have switched devices in between).
+inline void use_device(const tf_map* m) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != m->cfg.device) cudaSetDevice(m->cfg.device);
+}
+
 bool cam_ok(const tf_map* m, const tf_camera* c) { return c && c->width == m->W && c->height == m->H; }
 
 // Slot of a stored frame, or -1.  for_compute: work is about to be queued on the compute stream
@@ -641,6 +648,7 @@ int tf_reset(tf_map* m) {
 
 int tf_sync(tf_map* m) {
   if (!m) return TF_ERR_INVALID;
+  use_device(m);
   CUDA_OK(m, cudaStreamSynchronize(m->copy_stream));
   CUDA_OK(m, cudaStreamSynchronize(m->stream));
   prof_collect(m, 0);
@@ -649,6 +657,7 @@ int tf_sync(tf_map* m) {
 
 int tf_wait_upload(tf_map* m, int32_t frame_index) {
   if (!m) return TF_ERR_INVALID;
+  use_device(m);
   const int s = find_slot(m, frame_index, false);
   if (s < 0) return fail(m, TF_ERR_NOT_FOUND, "frame_index not in the frame store");
   // (the slot stays `pending` for the compute stream: waiting on a completed event costs nothing)
@@ -666,6 +675,7 @@ void* tf_stream(tf_map* m) { return m ? (void*)m->stream : nullptr; }
 int tf_upload_frame(tf_map* m, int32_t frame_index, const float* depth, const uint8_t* rgba,
                     const float* quality) {
   if (!m || !depth || frame_index < 0) return fail(m, TF_ERR_INVALID, "tf_upload_frame: bad argument");
+  use_device(m);
   const int s = acquire_slot(m, frame_index);
   FrameSlot& fsl = m->slots[s];
   const size_t nb = (size_t)m->npix * 4;
@@ -691,6 +701,7 @@ int tf_upload_frame(tf_map* m, int32_t frame_index, const float* depth, const ui
 
 int tf_upload_keyframe_rgb(tf_map* m, int32_t frame_index, const uint8_t* rgb, const uint8_t* color_valid) {
   if (!m || !rgb) return fail(m, TF_ERR_INVALID, "tf_upload_keyframe_rgb: bad argument");
+  use_device(m);
   const int s = find_slot(m, frame_index, false);
   if (s < 0) return fail(m, TF_ERR_NOT_FOUND, "frame_index not in the frame store (upload depth first)");
   FrameSlot& fsl = m->slots[s];
@@ -722,6 +733,7 @@ int tf_release_frame(tf_map* m, int32_t frame_index) {
 int tf_frame_device_ptrs(tf_map* m, int32_t frame_index, int has_color, void** depth, void** rgba,
                          void** quality) {
   if (!m || frame_index < 0) return fail(m, TF_ERR_INVALID, "tf_frame_device_ptrs: bad argument");
+  use_device(m);
   const int s = acquire_slot(m, frame_index);
   FrameSlot& fsl = m->slots[s];
   if (has_color) {
@@ -739,6 +751,7 @@ int tf_frame_device_ptrs(tf_map* m, int32_t frame_index, int has_color, void** d
 int tf_prepare(tf_map* m, int32_t frame_index, const tf_pose* pose, const tf_camera* cam, tf_chunk_id* ids_out,
                uint8_t* is_new_out, int64_t cap, int64_t* n_out) {
   if (!m || !pose || !n_out || !cam_ok(m, cam)) return fail(m, TF_ERR_INVALID, "tf_prepare: bad argument");
+  use_device(m);
   const int s = find_slot(m, frame_index);
   if (s < 0) return fail(m, TF_ERR_NOT_FOUND, "frame_index not in the frame store");
   CullParams cp;
@@ -773,6 +786,7 @@ int tf_integrate_group(tf_map* m, const tf_group_frame* frames, int32_t n_frames
                        const tf_chunk_id* ids, int64_t n, uint8_t* needs_update, float* quality_out) {
   if (!m || !frames || !cam_ok(m, cam) || n < 0 || (n > 0 && (!ids || !needs_update)))
     return fail(m, TF_ERR_INVALID, "tf_integrate_group: bad argument");
+  use_device(m);
   GroupParams gp;
   bool color[kMaxGroupFrames];
   if (int rc = build_group(m, frames, n_frames, cam, gp, color)) return rc;
@@ -806,6 +820,7 @@ int tf_integrate(tf_map* m, int32_t frame_index, int use_color, const tf_pose* p
 
 int tf_remove_chunks(tf_map* m, const tf_chunk_id* ids, int64_t n) {
   if (!m || n < 0 || (n > 0 && !ids)) return fail(m, TF_ERR_INVALID, "tf_remove_chunks: bad argument");
+  use_device(m);
   if (n == 0) return TF_OK;
   if (int rc = upload_ids(m, ids, n)) return rc;
   const int grid = (int)std::min<int64_t>(m->grid, (n + kThreads - 1) / kThreads);
@@ -1047,6 +1062,7 @@ int tf_integrate_frame(tf_map* m, int32_t frame_index, int use_color, const tf_p
                        tf_frame_stats* stats, tf_chunk_id* ids_out, uint8_t* is_new_out, uint8_t* updated_out,
                        float* quality_out, int64_t cap) {
   if (!m || !pose || !cam_ok(m, cam) || cap < 0) return fail(m, TF_ERR_INVALID, "tf_integrate_frame: bad argument");
+  use_device(m);
   tf_group_frame g;
   g.frame_index = frame_index;
   g.use_color = use_color;
@@ -1129,6 +1145,7 @@ static int flush_batch(tf_map* m, std::vector<PendingItem>& pend) {
 int tf_integrate_batch(tf_map* m, const tf_batch_item* items, int64_t n_items, const tf_camera* cam) {
   if (!m || n_items < 0 || (n_items > 0 && !items) || !cam_ok(m, cam))
     return fail(m, TF_ERR_INVALID, "tf_integrate_batch: bad argument");
+  use_device(m);
   int max_frames = 1;
   bool any_lists = false, any_ids = false;
   for (int64_t k = 0; k < n_items; k++) {
@@ -1276,6 +1293,7 @@ extern "C" int tf_debug_timeline(tf_map* m, unsigned long long* out32, int reset
 
 int tf_has_chunk(tf_map* m, tf_chunk_id id) {
   if (!m) return TF_ERR_INVALID;
+  use_device(m);
   if (int rc = lookup_ids(m, &id, 1, false)) return rc;
   int slot = -1;
   CUDA_OK(m, cudaMemcpy(&slot, m->cb.list_slots, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1286,6 +1304,7 @@ int64_t tf_chunk_count(tf_map* m) { return m ? m->n_live : TF_ERR_INVALID; }
 
 int tf_list_chunks(tf_map* m, tf_chunk_id* out, int64_t cap, int64_t* n_out) {
   if (!m || !n_out) return fail(m, TF_ERR_INVALID, "tf_list_chunks: bad argument");
+  use_device(m);
   *n_out = m->n_live;
   if (m->n_live == 0) return TF_OK;
   if (cap < m->n_live || !out) return fail(m, TF_ERR_CAPACITY, "tf_list_chunks: output capacity too small");
@@ -1306,6 +1325,7 @@ int tf_list_chunks(tf_map* m, tf_chunk_id* out, int64_t cap, int64_t* n_out) {
 
 int tf_download_chunks(tf_map* m, const tf_chunk_id* ids, int64_t n, float* sdf, float* weight, uint16_t* color) {
   if (!m || n < 0 || (n > 0 && !ids)) return fail(m, TF_ERR_INVALID, "tf_download_chunks: bad argument");
+  use_device(m);
   if (!m->dl_sdf) {
     m->dl_cap = 8192;
     CUDA_OK(m, dmalloc(&m->dl_sdf, (size_t)m->dl_cap * 512));
@@ -1372,6 +1392,7 @@ static int ensure_atlas(tf_map* m) {
 
 int tf_atlas_update(tf_map* m, const tf_patch_desc* patches, int64_t n) {
   if (!m || n < 0 || (n > 0 && !patches)) return fail(m, TF_ERR_INVALID, "tf_atlas_update: bad argument");
+  use_device(m);
   if (n == 0) return TF_OK;
   if (int rc = ensure_atlas(m)) return rc;
   std::vector<PatchDev> pd((size_t)n);
@@ -1403,6 +1424,7 @@ int tf_atlas_update(tf_map* m, const tf_patch_desc* patches, int64_t n) {
 int tf_atlas_download(tf_map* m, uint64_t hot_start, uint64_t hot_end, uint8_t* rgb_out) {
   if (!m || !rgb_out || hot_end < hot_start || hot_end > (uint64_t)kAtlasDim * kAtlasDim)
     return fail(m, TF_ERR_INVALID, "tf_atlas_download: bad range");
+  use_device(m);
   if (int rc = ensure_atlas(m)) return rc;
   const size_t nb = (size_t)(hot_end - hot_start) * 3;
   CUDA_OK(m, cudaMemcpyAsync(rgb_out, m->atlas + hot_start * 3, nb, cudaMemcpyDeviceToHost, m->stream));
@@ -1418,6 +1440,7 @@ int tf_patch_texcoords(tf_map* m, int32_t frame_index, const tf_pose* world_to_c
   if (!m || !world_to_camera || !cam_ok(m, cam) || n_patches < 0 ||
       (n_patches > 0 && (!vertex_offsets || !vertices || !colors || !texcoord_out || !texcolor_out || !results)))
     return fail(m, TF_ERR_INVALID, "tf_patch_texcoords: bad argument");
+  use_device(m);
   if (n_patches == 0) return TF_OK;
   const int s = find_slot(m, frame_index);
   if (s < 0 || !m->slots[s].has_rgb) return fail(m, TF_ERR_NOT_FOUND, "tf_patch_texcoords: key-frame rgb not in the frame store");
@@ -1474,6 +1497,7 @@ int tf_debug_project(tf_map* m, const float* c, const float* cz, int64_t n, floa
                      int32_t* u_exact, uint8_t* accepted) {
   if (!m || !c || !cz || !u_fast || !u_exact || !accepted || n <= 0 || n > (1 << 26))
     return fail(m, TF_ERR_INVALID, "tf_debug_project: bad argument");
+  use_device(m);
   float *dc = nullptr, *dz = nullptr;
   int *duf = nullptr, *due = nullptr;
   unsigned char* da = nullptr;
