@@ -340,20 +340,34 @@ def main():
         assert rc == 0, L.tf_last_error(m.h)
         return st.n_chunks
 
+    # Multi-GPU: rank 0 ingests frame i+1 (H2D on the map's copy stream) and the planes are broadcast
+    # over NVLink into every rank's frame store ON THAT STREAM, i.e. behind the copy and next to the
+    # kernels of frame i; the compute stream waits for the broadcast's event before frame i+1.
+    bcast_ready = {}
+    if dist is not None:
+        ext_copy = torch.cuda.ExternalStream(m.copy_stream(), device=dev)
+        ext_comp = torch.cuda.ExternalStream(m.stream(), device=dev)
+
+    def stage_broadcast(i):
+        fr = frames[i]
+        d_ptr, c_ptr, q_ptr = m.frame_device_ptrs(fr.index, fr.is_keyframe)
+        if rank == 0:
+            upload(i)
+        with torch.cuda.stream(ext_copy):
+            for ptr in [d_ptr] + ([c_ptr, q_ptr] if fr.is_keyframe else []):
+                dist.broadcast(dev_tensor(torch, ptr, cam.height * cam.width, local_rank), src=0)
+            ev = torch.cuda.Event()
+            ev.record(ext_copy)
+        bcast_ready[i] = ev
+
     def e2e_step(i):
         if dist is not None:
-            # rank 0 ingests the frame; its planes are broadcast over NVLink into every rank's store
-            fr = frames[i]
-            d_ptr, c_ptr, q_ptr = m.frame_device_ptrs(fr.index, fr.is_keyframe)
-            if rank == 0:
-                upload(i)
-                m.sync()
-            planes = [(d_ptr, 4)] + ([(c_ptr, 4), (q_ptr, 4)] if fr.is_keyframe else [])
-            for ptr, _ in planes:
-                t = dev_tensor(torch, ptr, cam.height * cam.width, local_rank)
-                dist.broadcast(t, src=0)
-            torch.cuda.synchronize()
-            return fuse(i)
+            j = (i + 1) % nf
+            stage_broadcast(j)                      # in flight during this frame's kernels
+            ext_comp.wait_event(bcast_ready.pop(i))  # (device-side wait: frame i has arrived)
+            n = fuse(i)
+            bcast_ready[j].synchronize()             # ... and finished inside this timed step
+            return n
         j = (i + 1) % nf
         upload(j)  # next frame's copy, in flight during this frame's kernels
         n = fuse(i)
@@ -365,6 +379,9 @@ def main():
     if dist is None:
         upload(0)
         m.sync()
+    else:
+        stage_broadcast(0)
+        torch.cuda.synchronize()
     for _ in range(args.warmup):
         e2e_step(k % nf)
         k += 1
@@ -388,7 +405,9 @@ def main():
            "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / args.steps,
            "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / args.steps,
            "ms_per_step": 1e3 * e2e_s / args.steps, "median_ms_per_step": 1e3 * float(np.median(step_s)),
-           "mode": "double buffered: upload(i+1) | fuse(i) | wait_upload(i+1), host buffers page-locked"}
+           "mode": ("double buffered: upload(i+1) | fuse(i) | wait_upload(i+1), host buffers page-locked" if dist is None else
+                    "double buffered: rank 0 uploads frame i+1 and all ranks broadcast it (NCCL) on the copy stream | "
+                    "fuse(i) on every rank's shard | wait for the broadcast")}
     m.close()
 
     if rank != 0:

@@ -257,6 +257,9 @@ typedef struct {
 int tf_get_counters(tf_map* m, tf_counters* out);
 /* CUDA stream of the map as a cudaStream_t cast to void* (for event timing by the caller) */
 void* tf_stream(tf_map* m);
+/* cudaStream_t of the frame uploads: a collective that must follow an upload (frame broadcast to the
+ * other ranks) can be queued on it instead of waiting on the host. */
+void* tf_copy_stream(tf_map* m);
 /* device time (ms) spent in the integrate kernel since the last call with reset != 0;
  * measured with CUDA events on the map's stream when enabled via tf_set_profiling. */
 int tf_set_profiling(tf_map* m, int level /* 0 off, 1 integrate kernel, 2 every pipeline stage */);

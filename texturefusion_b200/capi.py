@@ -23,7 +23,7 @@ EXPORTS = [
     "tf_prepare", "tf_integrate", "tf_integrate_group", "tf_remove_chunks", "tf_integrate_frame",
     "tf_integrate_batch", "tf_has_chunk", "tf_chunk_count", "tf_list_chunks", "tf_download_chunks",
     "tf_atlas_alloc_slot", "tf_atlas_update", "tf_atlas_download", "tf_atlas_patch_size", "tf_patch_texcoords", "tf_sync", "tf_wait_upload",
-    "tf_get_counters", "tf_stream", "tf_set_profiling", "tf_get_kernel_time", "tf_get_stage_times", "tf_debug_project",
+    "tf_get_counters", "tf_stream", "tf_copy_stream", "tf_set_profiling", "tf_get_kernel_time", "tf_get_stage_times", "tf_debug_project",
 ]
 
 
@@ -130,6 +130,8 @@ def load() -> C.CDLL:
     L.tf_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.tf_stream.argtypes = [vp]
     L.tf_stream.restype = vp
+    L.tf_copy_stream.argtypes = [vp]
+    L.tf_copy_stream.restype = vp
     L.tf_set_profiling.argtypes = [vp, C.c_int]
     L.tf_get_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]
     L.tf_get_stage_times.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
@@ -419,6 +421,9 @@ class Map:
 
     def stream(self) -> int:
         return int(self.L.tf_stream(self.h) or 0)
+
+    def copy_stream(self) -> int:
+        return int(self.L.tf_copy_stream(self.h) or 0)
 
     def set_profiling(self, level):
         self._check(self.L.tf_set_profiling(self.h, int(level)))

@@ -668,6 +668,8 @@ int tf_wait_upload(tf_map* m, int32_t frame_index) {
   }
 }
 
+void* tf_copy_stream(tf_map* m) { return m ? (void*)m->copy_stream : nullptr; }
+
 void* tf_stream(tf_map* m) { return m ? (void*)m->stream : nullptr; }
 
 // ---- frame store ---------------------------------------------------------------------------
