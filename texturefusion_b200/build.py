@@ -46,5 +46,18 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def build_timeline_variant() -> str:
+    """The instrumented library tools/timeline.py needs (device + host time stamps, -DTF_TIMELINE);
+    written to build/variants/timeline.so, selected with TEXFUSION_B200_LIB."""
+    out = os.path.join(os.path.dirname(_PKG), "build", "variants", "timeline.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.check_call([_nvcc(), *NVCC_FLAGS, "-DTF_TIMELINE", "-o", out, os.path.join(_CSRC, "tf_capi.cu")])
+    return out
+
+
 if __name__ == "__main__":
-    print(build_library(force=True, verbose=True))
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "timeline":
+        print(build_timeline_variant())
+    else:
+        print(build_library(force=True, verbose=True))

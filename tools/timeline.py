@@ -1,7 +1,7 @@
 """Device timeline of the fused per-frame chain (needs a -DTF_TIMELINE build of the library):
 
-  nvcc <flags of texturefusion_b200/build.py> -DTF_TIMELINE -o build/variants/timeline.so texturefusion_b200/csrc/tf_capi.cu
-  TEXFUSION_B200_LIB=build/variants/timeline.so python tools/timeline.py [--steps 100]
+  python -m texturefusion_b200.build timeline          # -> build/variants/timeline.so
+  TEXFUSION_B200_LIB=build/variants/timeline.so python tools/timeline.py [--steps 100] [--lists] [--res 0.04]
 
 Prints, per kernel, the mean (over frames) of: first block start, first / … return from the
 programmatic-dependent-launch wait, end of the last block's main work and end of its tail, in
