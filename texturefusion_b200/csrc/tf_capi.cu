@@ -851,9 +851,11 @@ struct FrameArgs {
   ExportArgs ex;
 };
 
+// export_kernel is PCIe-bound (eight blocks already saturate the link) and every block ends with a
+// system-scope fence: a small grid finishes earlier than one block per SM.
 static int export_grid(const tf_map* m) {
   static const int g = [] { const char* e = getenv("TEXFUSION_B200_EXPORT_GRID"); return e ? atoi(e) : 0; }();
-  return g > 0 ? g : m->sm_count;
+  return g > 0 ? g : std::min(8, m->sm_count);
 }
 
 static void launch_frame_kernels(tf_map* m, FrameArgs& a, bool profile = false) {
