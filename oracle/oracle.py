@@ -1,9 +1,18 @@
-"""ctypes binding of oracle/libtexfusion_oracle.so (CPU oracle — test infrastructure only)."""
+"""ctypes binding of the CPU checkers (test infrastructure only):
+
+  impl="port"      oracle/libtexfusion_oracle.so — the AVX2 restatement (tf_oracle.cpp)
+  impl="ref"       oracle/_ref/libtexfusion_ref.so — the reference's OWN sources compiled against
+                   oracle/eigen_standin (ref_driver.cpp); built here, where /root/reference exists,
+                   and shipped prebuilt to the GPU box
+  impl="ref_l2r"   the same with left-to-right 3-term products (Eigen 3.2 association)
+"""
 from __future__ import annotations
 
 import ctypes as C
 import os
+import shutil
 import subprocess
+import tempfile
 
 import numpy as np
 
@@ -33,10 +42,57 @@ class _Cam(C.Structure):
                 ("far_plane", C.c_float)]
 
 
+def ref_lib_path(impl: str = "ref") -> str:
+    return os.path.join(_HERE, "_ref", "libtexfusion_ref.so" if impl == "ref" else "libtexfusion_ref_l2r.so")
+
+
+def have_ref(impl: str = "ref") -> bool:
+    return os.path.exists(ref_lib_path(impl))
+
+
+def build_ref() -> bool:
+    """(Re)builds oracle/_ref from the reference tree when it is present; True if the library exists."""
+    if os.path.isdir("/root/reference/Structure"):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    return have_ref()
+
+
+_REF_LIBS = {}
+_REF_TMP = None
+
+
+def _ref_lib(impl: str, res: float):
+    """One loaded copy of the reference library per (impl, resolution): ChunkManager::GetIDAt and the
+    mesher keep resolution-dependent function-local statics (Structure/ChunkManager.h:197-203)."""
+    global _REF_TMP
+    key = (impl, float(np.float32(res)))
+    if key not in _REF_LIBS:
+        src = ref_lib_path(impl)
+        if not os.path.exists(src):
+            raise FileNotFoundError(f"{src} not built (make -C oracle ref needs /root/reference)")
+        if _REF_TMP is None:
+            _REF_TMP = tempfile.mkdtemp(prefix="tf_ref_")
+        dst = os.path.join(_REF_TMP, f"libtexfusion_{impl}_{len(_REF_LIBS)}.so")
+        shutil.copyfile(src, dst)
+        L = C.CDLL(dst)
+        _declare(L)
+        L.tfo_impl.restype = C.c_char_p
+        L.tfo_mesh_chunks.argtypes = [C.c_void_p] * 9 + [C.c_int64, C.c_int64]
+        _REF_LIBS[key] = L
+    return _REF_LIBS[key]
+
+
 def _lib():
     global _LIB
     if _LIB is None:
         L = C.CDLL(build_oracle())
+        _declare(L, full=True)
+        _LIB = L
+    return _LIB
+
+
+def _declare(L, full=False):
+    if True:
         vp, f32p, u8p, i32p = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
         L.tfo_create.restype = vp
         L.tfo_create.argtypes = [C.c_float, f32p, C.c_int]
@@ -64,16 +120,16 @@ def _lib():
         L.tfo_get_observation.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int, f32p]
         L.tfo_meshes_to_update.restype = C.c_int64
         L.tfo_meshes_to_update.argtypes = [vp, vp, C.c_int64]
+        L.tfo_truncation_distance.restype = C.c_float
+        L.tfo_truncation_distance.argtypes = [f32p, C.c_float]
+        L.tfo_centroids.argtypes = [vp, vp, vp]
+        if not full:
+            return
         L.tfo_atlas_patch_size.argtypes = [vp, i32p, i32p]
         L.tfo_atlas_alloc_slot.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]
         L.tfo_atlas_update.argtypes = [vp, C.c_uint64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.tfo_atlas_download.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
         L.tfo_patch_texcoords.argtypes = [vp, vp, vp, C.POINTER(_Cam), C.c_int64, vp, vp, vp, vp, vp, vp]
-        L.tfo_truncation_distance.restype = C.c_float
-        L.tfo_truncation_distance.argtypes = [f32p, C.c_float]
-        L.tfo_centroids.argtypes = [vp, vp, vp]
-        _LIB = L
-    return _LIB
 
 
 def _p(a):
@@ -89,9 +145,10 @@ def _cam(cam) -> _Cam:
     return _Cam(cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height, cam.near, cam.far)
 
 
-def truncation_distance(z: float, trunc=DEFAULT_TRUNC) -> float:
+def truncation_distance(z: float, trunc=DEFAULT_TRUNC, impl: str = "port") -> float:
     t = (C.c_float * 5)(*trunc)
-    return float(_lib().tfo_truncation_distance(t, C.c_float(z)))
+    L = _lib() if impl == "port" else _ref_lib(impl, 0.0)
+    return float(L.tfo_truncation_distance(t, C.c_float(z)))
 
 
 def patch_texcoords(rgb, depth, world_to_camera, cam, offsets, vertices, colors):
@@ -113,8 +170,9 @@ def patch_texcoords(rgb, depth, world_to_camera, cam, offsets, vertices, colors)
 class OracleMap:
     """CPU restatement of chisel::Chisel's fusion path (prepare / integrate / finalize / atlas)."""
 
-    def __init__(self, res: float, trunc=DEFAULT_TRUNC, threads: int = 1):
-        self.L = _lib()
+    def __init__(self, res: float, trunc=DEFAULT_TRUNC, threads: int = 1, impl: str = "port"):
+        self.impl = impl
+        self.L = _lib() if impl == "port" else _ref_lib(impl, res)
         self.res = float(np.float32(res))
         self.h = self.L.tfo_create(C.c_float(res), (C.c_float * 5)(*trunc), threads)
 
@@ -226,6 +284,23 @@ class OracleMap:
         out = np.empty((3, 512), np.float32)
         self.L.tfo_centroids(self.h, _p(_pose(pose)), _p(out))
         return out
+
+    def mesh_chunks(self, ids):
+        """ChunkManager::GenerateMeshEfficient per chunk (impl "ref" only): offsets + concatenated
+        vertices / normals / colours / indices."""
+        ids = np.ascontiguousarray(ids, np.int32).reshape(-1, 3)
+        n = len(ids)
+        voff = np.zeros(n + 1, np.int64)
+        ioff = np.zeros(n + 1, np.int64)
+        self.L.tfo_mesh_chunks(self.h, _p(ids), n, _p(voff), _p(ioff), None, None, None, None, 0, 0)
+        nv, ni = int(voff[-1]), int(ioff[-1])
+        vert = np.empty((max(nv, 1), 3), np.float32)
+        norm = np.empty((max(nv, 1), 3), np.float32)
+        col = np.empty((max(nv, 1), 3), np.float32)
+        idx = np.empty(max(ni, 1), np.int32)
+        rc = self.L.tfo_mesh_chunks(self.h, _p(ids), n, _p(voff), _p(ioff), _p(vert), _p(norm), _p(col), _p(idx), nv, ni)
+        assert rc == 0
+        return voff, ioff, vert[:nv], norm[:nv], col[:nv], idx[:ni]
 
     # atlas
     def atlas_patch_size(self):
