@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define TF_ABI_VERSION 1
+#define TF_ABI_VERSION 2
 
 enum {
   TF_OK = 0,
@@ -84,6 +84,12 @@ typedef struct {
   int32_t max_frames;     /* frame-store slots, allocated up front: 4 B (16 B with use_color) per
                              pixel and slot; 0 = default (32) */
   int32_t width, height;  /* frame size of the store; 0 = 640x480 */
+  int32_t dot3_order;     /* association of the reference's 3-term Eigen products (Rt * v at
+                             ProjectionIntegrator.cpp:88-89, Structure/Chisel.cpp:67-69,
+                             Structure/ChunkManager.h:429-453,521-524), which depends on the Eigen the
+                             reference was built with: 0 = Eigen >= 3.3, x0 + (x1 + x2);
+                             1 = Eigen 3.2, (x0 + x1) + x2.  tools/ref_golden/probe_eigen_order.cpp
+                             prints the value for an installed Eigen. */
 } tf_config;
 
 /* chisel::Chisel::Chisel + ChunkManager ctor (Structure/Chisel.cpp:38-41). */
@@ -93,6 +99,10 @@ void tf_destroy(tf_map* m);
 const char* tf_last_error(const tf_map* m);
 /* Chisel::Reset (Structure/Chisel.cpp:47-50): drop all chunks, keep frames and atlas. */
 int tf_reset(tf_map* m);
+/* ProjectionIntegrator::SetTruncator / SetWeighter (GCFusion/MobileFusion.h:245-249): the reference
+ * reads them on every voxelUpdateSIMD call (ProjectionIntegrator.cpp:90-92), so they can change
+ * between calls; takes effect from the next prepare / integrate call. */
+int tf_set_truncation(tf_map* m, const tf_truncation* t);
 
 /* pinned host memory for frame / result buffers */
 void* tf_host_alloc(size_t bytes);
@@ -103,13 +113,17 @@ void tf_host_free(void* p);
  * (GCSLAM/frame.h:35-66, GCFusion/MobileFusion.cpp:147-162).  depth: float32 metres,
  * width*height; rgba: 4 bytes per pixel, A = colour-valid (1/0); quality: float32.
  * rgba/quality may be NULL (depth-only local frame, GCFusion/MobileFusion.cpp:198-202).
- * Re-uploading a frame_index overwrites it. */
+ * Re-uploading a frame_index replaces it: planes that are not passed are absent afterwards.
+ * When the store is full the least-recently-used frame that is not pinned (see
+ * tf_upload_keyframe_rgb) is replaced; TF_ERR_CAPACITY if every slot is pinned. */
 int tf_upload_frame(tf_map* m, int32_t frame_index, const float* depth,
                     const uint8_t* rgba_or_null, const float* quality_or_null);
 /* Key-frame colour as the reference stores it: Frame::rgb (8UC3) + colorValidFlag (8U).
  * Keeps rgb for the atlas (Patch::SetImage, Structure/Patch.cpp:172-175) and packs the
  * RGBA plane on the device — replaces the scalar pack loop GCFusion/MobileFusion.cpp:151-162
- * (color_valid == NULL: alpha = 1 everywhere, as IntegrateFrame :237-242). */
+ * (color_valid == NULL: alpha = 1 everywhere, as IntegrateFrame :237-242).  The slot is pinned —
+ * never evicted — until tf_release_frame: the reference keeps every key-frame's rgb for
+ * Atlas::UpdateBuffer, so size tf_config.max_frames for the key-frames that stay texturable. */
 int tf_upload_keyframe_rgb(tf_map* m, int32_t frame_index, const uint8_t* rgb,
                            const uint8_t* color_valid_or_null);
 int tf_release_frame(tf_map* m, int32_t frame_index);

@@ -43,6 +43,11 @@ class _Cam(C.Structure):
 
 
 def ref_lib_path(impl: str = "ref") -> str:
+    """TF_REF_LIB overrides the library (a build against the real Eigen, tools/ref_golden/);
+    it serves as impl "ref", or as "ref_l2r" when TF_REF_ORDER=l2r."""
+    ov = os.environ.get("TF_REF_LIB")
+    if ov and (impl == "ref_l2r") == (os.environ.get("TF_REF_ORDER") == "l2r"):
+        return ov
     return os.path.join(_HERE, "_ref", "libtexfusion_ref.so" if impl == "ref" else "libtexfusion_ref_l2r.so")
 
 
@@ -87,8 +92,16 @@ def _lib():
     if _LIB is None:
         L = C.CDLL(build_oracle())
         _declare(L, full=True)
+        L.tfo_impl.restype = C.c_char_p
+        L.tfo_set_dot3_order.argtypes = [C.c_int]
         _LIB = L
     return _LIB
+
+
+def set_dot3_order(left_to_right: bool):
+    """Association of the restatement's 3-term products (process-wide; impl "port" only — the
+    reference build has one library per order: impl "ref" / "ref_l2r")."""
+    _lib().tfo_set_dot3_order(1 if left_to_right else 0)
 
 
 def _declare(L, full=False):

@@ -21,9 +21,16 @@ INT_MIN = -(2 ** 31)
 SENTINEL = f32(-99999999999.0)
 
 
+DOT3_LEFT_TO_RIGHT = False  # True: Eigen 3.2 association (see oracle/eigen_standin/Eigen/Core)
+
+
 def dot3(a0, b0, a1, b1, a2, b2):
-    """Eigen fixed-size 3-vector inner product: x0 + (x1 + x2), every op rounded to float."""
-    return f32(f32(f32(a0) * f32(b0)) + f32(f32(f32(a1) * f32(b1)) + f32(f32(a2) * f32(b2))))
+    """Eigen fixed-size 3-vector inner product, every op rounded to float: x0 + (x1 + x2) from
+    Eigen 3.3 on, (x0 + x1) + x2 with Eigen 3.2."""
+    p0, p1, p2 = f32(f32(a0) * f32(b0)), f32(f32(a1) * f32(b1)), f32(f32(a2) * f32(b2))
+    if DOT3_LEFT_TO_RIGHT:
+        return f32(f32(p0 + p1) + p2)
+    return f32(p0 + f32(p1 + p2))
 
 
 def rne_x86(x) -> int:

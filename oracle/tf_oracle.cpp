@@ -6,18 +6,24 @@
 // (tests/, __graft_entry__.smoke) and to serve as the CPU baseline of bench.py;
 // nothing under texturefusion_b200/ may link, import or call it.
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
-// and cannot be compiled here (Eigen / OpenCV / Sophus / Pangolin headers are absent), so
-// this restatement is validated only against (i) an independent scalar restatement in
-// oracle/scalar_ref.py and (ii) hand-computed known-answer cases in tests/.
+// HOW IT IS PINNED: the reference ships no tests, golden vectors or fixtures for this path.  Its
+// fusion sources do compile here once Eigen (absent from this image) is replaced by the stand-in
+// in oracle/eigen_standin: oracle/_ref/libtexfusion_ref.so (oracle/Makefile, ref_driver.cpp) is the
+// reference's own ProjectionIntegrator.cpp / ChunkManager.{h,cpp} / Chunk / truncator / weighter /
+// camera code, and tests/test_ref_cpu.py checks this restatement against it bit for bit (chunk
+// lists in order, flags, quality sums, every voxel) at 40/20/10/5 mm; tests/golden/*.npz are
+// generated from that library.  What stays unverifiable here is the one thing the stand-in has to
+// choose: the association order of Eigen's 3-term products (runtime switch below;
+// tools/ref_golden/ is the recipe for a machine that has Eigen).  Also checked against an
+// independent scalar restatement (oracle/scalar_ref.py) and hand-computed known-answer cases.
 //
 // Arithmetic rules it follows (see DESIGN.md "Arithmetic contract"):
 //   * the reference is built with -mavx2 and WITHOUT -mfma (CMakeLists.txt:57-58): every
 //     float op is a separate IEEE binary32 op; this file is compiled with
 //     -mno-fma -ffp-contract=off and uses the same AVX2 intrinsics for the vector parts.
 //   * Eigen fixed-size 3-vector inner products (coefficient-based lazy product ->
-//     redux_novec_unroller<0,3>) associate as a0*b0 + (a1*b1 + a2*b2).  Define
-//     TF_DOT3_LEFT_TO_RIGHT to get (a0*b0 + a1*b1) + a2*b2 instead.
+//     redux_novec_unroller<0,3>) associate as a0*b0 + (a1*b1 + a2*b2) from Eigen 3.3 on;
+//     Eigen 3.2 accumulates (a0*b0 + a1*b1) + a2*b2.  tfo_set_dot3_order switches (process-wide).
 //   * PinholeCamera::GetFx/GetFy/GetCx/GetCy return int
 //     (3rd_party/open_chisel/camera/PinholeCamera.h:46-49).
 #include <immintrin.h>
@@ -91,15 +97,10 @@ struct Map {
   alignas(32) float cen[3][512];
 };
 
-#ifdef TF_DOT3_LEFT_TO_RIGHT
+int g_dot3_l2r = 0;  // tfo_set_dot3_order
 inline float dot3(float a0, float b0, float a1, float b1, float a2, float b2) {
-  return (a0 * b0 + a1 * b1) + a2 * b2;
+  return g_dot3_l2r ? (a0 * b0 + a1 * b1) + a2 * b2 : a0 * b0 + (a1 * b1 + a2 * b2);
 }
-#else
-inline float dot3(float a0, float b0, float a1, float b1, float a2, float b2) {
-  return a0 * b0 + (a1 * b1 + a2 * b2);
-}
-#endif
 
 // pose: column-major 4x4, camera->world.  R(i,j) = m[j*4+i]; Rt(i,j) = R(j,i).
 inline float R(const float* m, int i, int j) { return m[j * 4 + i]; }
@@ -440,6 +441,10 @@ void parallel_for(int64_t n, int threads_cfg, F&& f) {
 extern "C" {
 
 struct tfo_map;  // opaque alias of Map
+
+const char* tfo_impl() { return "restatement (tf_oracle.cpp)"; }
+// 0: x0 + (x1 + x2) (Eigen >= 3.3), 1: (x0 + x1) + x2 (Eigen 3.2).  Process-wide.
+void tfo_set_dot3_order(int left_to_right) { g_dot3_l2r = left_to_right ? 1 : 0; }
 
 tfo_map* tfo_create(float res, const float* trunc5, int threads) {
   Map* m = new Map;

@@ -272,3 +272,17 @@ def test_threaded_oracle_equals_serial():
     sa, sb = a.download_chunks(ia), b.download_chunks(ia)
     for x, y in zip(sa, sb):
         assert np.array_equal(x, y)
+
+
+def test_probe_against_standin(tmp_path):
+    """tools/ref_golden/probe_eigen_order.cpp (the program that tells a maintainer which
+    tf_config.dot3_order their Eigen needs) detects both orders of the Eigen stand-in."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tools", "ref_golden", "probe_eigen_order.cpp")
+    inc = os.path.join(root, "oracle", "eigen_standin")
+    for flag, want in (([], 0), (["-DEIGEN_STANDIN_LEFT_TO_RIGHT"], 1)):
+        exe = str(tmp_path / f"probe{want}")
+        subprocess.check_call(["g++", "-O3", "-mavx2", "-mno-fma", "-ffp-contract=off", *flag, f"-I{inc}", src, "-o", exe])
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+        assert f"tf_config.dot3_order = {want}" in out and "WARNING" not in out

@@ -18,7 +18,7 @@ TF_OK, TF_ERR_INVALID, TF_ERR_CUDA, TF_ERR_CAPACITY, TF_ERR_NOT_FOUND, TF_ERR_AT
 DEFAULT_TRUNC = (0.0019, 0.00152, 0.001504, 6.0, 1.0)
 
 EXPORTS = [
-    "tf_create", "tf_destroy", "tf_last_error", "tf_reset", "tf_host_alloc", "tf_host_free",
+    "tf_create", "tf_destroy", "tf_last_error", "tf_reset", "tf_set_truncation", "tf_host_alloc", "tf_host_free",
     "tf_upload_frame", "tf_upload_keyframe_rgb", "tf_release_frame", "tf_frame_device_ptrs",
     "tf_prepare", "tf_integrate", "tf_integrate_group", "tf_remove_chunks", "tf_integrate_frame",
     "tf_integrate_batch", "tf_has_chunk", "tf_chunk_count", "tf_list_chunks", "tf_download_chunks",
@@ -50,7 +50,7 @@ class Config(C.Structure):
     _fields_ = [("chunk_dim", C.c_int32), ("voxel_res", C.c_float), ("use_color", C.c_int32),
                 ("trunc", Truncation), ("device", C.c_int32), ("n_ranks", C.c_int32), ("rank", C.c_int32),
                 ("max_chunks", C.c_int64), ("max_frames", C.c_int32), ("width", C.c_int32),
-                ("height", C.c_int32)]
+                ("height", C.c_int32), ("dot3_order", C.c_int32)]
 
 
 class GroupFrame(C.Structure):
@@ -100,6 +100,7 @@ def load() -> C.CDLL:
     L.tf_last_error.argtypes = [vp]
     L.tf_last_error.restype = C.c_char_p
     L.tf_reset.argtypes = [vp]
+    L.tf_set_truncation.argtypes = [vp, C.POINTER(Truncation)]
     L.tf_host_alloc.argtypes = [C.c_size_t]
     L.tf_host_alloc.restype = vp
     L.tf_host_free.argtypes = [vp]
@@ -192,11 +193,11 @@ class Map:
     """Thin object wrapper over a tf_map handle.  Methods mirror the C ABI one to one."""
 
     def __init__(self, voxel_res: float, *, use_color=True, trunc=DEFAULT_TRUNC, device=0, n_ranks=1, rank=0,
-                 max_chunks=0, max_frames=0, width=640, height=480):
+                 max_chunks=0, max_frames=0, width=640, height=480, dot3_order=0):
         self.L = load()
         self.h = C.c_void_p()
         cfg = Config(8, voxel_res, int(use_color), Truncation(*trunc), device, n_ranks, rank, max_chunks,
-                     max_frames, width, height)
+                     max_frames, width, height, dot3_order)
         rc = self.L.tf_create(C.byref(self.h), C.byref(cfg))
         if rc != TF_OK:
             msg = self.L.tf_last_error(None).decode()
@@ -221,6 +222,9 @@ class Map:
         if rc < 0:
             raise TexFusionError(rc, self.L.tf_last_error(self.h).decode())
         return rc
+
+    def set_truncation(self, trunc):
+        self._check(self.L.tf_set_truncation(self.h, C.byref(Truncation(*trunc))))
 
     # frame store -----------------------------------------------------------------------
     def upload_frame(self, frame_index, depth, rgba=None, quality=None):

@@ -40,6 +40,8 @@ struct FrameSlot {
   unsigned char* valid = nullptr;
   cudaEvent_t ready = nullptr;  // recorded on the copy stream after the slot's uploads
   bool pending = false;         // uploads in flight: consumers on the compute stream wait for `ready`
+  bool read_by_compute = false; // kernels that read the slot were queued since its last upload
+  bool pinned = false;          // key-frame rgb kept for the atlas: not evictable until tf_release_frame
 };
 
 struct EventPair {
@@ -67,6 +69,7 @@ struct tf_map {
   int W = 0, H = 0, npix = 0;
   cudaStream_t stream = nullptr;       // all kernels and read-backs
   cudaStream_t copy_stream = nullptr;  // frame uploads: the next frame's H2D copy overlaps the current frame's kernels
+  cudaEvent_t reuse_ev = nullptr;      // orders an overwriting upload behind the kernels that read the slot
   std::string err;
   float* slab_depth = nullptr;          // frame store: depth planes of all slots
   unsigned char* slab_color = nullptr;  // rgba | quality | rgb | valid planes of all slots
@@ -218,26 +221,46 @@ int find_slot(tf_map* m, int32_t frame_index, bool for_compute = true) {
   if (it == m->frame_to_slot.end()) return -1;
   FrameSlot& fsl = m->slots[it->second];
   fsl.last_use = ++m->use_clock;
-  if (for_compute && fsl.pending) {
-    cudaStreamWaitEvent(m->stream, fsl.ready, 0);
-    fsl.pending = false;
+  if (for_compute) {
+    fsl.read_by_compute = true;
+    if (fsl.pending) {
+      cudaStreamWaitEvent(m->stream, fsl.ready, 0);
+      fsl.pending = false;
+    }
   }
   return it->second;
 }
 
-// Slot for frame_index: existing, free, or the least-recently-used one.
+// Before the copy stream overwrites a slot that queued kernels may still be reading (a re-upload
+// of the same index, or a slot taken over from an evicted frame): order the copy behind them.
+void guard_overwrite(tf_map* m, FrameSlot& fsl) {
+  if (!fsl.read_by_compute) return;
+  cudaEventRecord(m->reuse_ev, m->stream);
+  cudaStreamWaitEvent(m->copy_stream, m->reuse_ev, 0);
+  fsl.read_by_compute = false;
+}
+
+// Slot for frame_index: existing, free, or the least-recently-used one that is not pinned
+// (-1: every slot holds a pinned key-frame).
 int acquire_slot(tf_map* m, int32_t frame_index) {
   int s = find_slot(m, frame_index, false);
   if (s >= 0) return s;
   int best = -1;
   for (int i = 0; i < (int)m->slots.size(); i++) {
     if (m->slots[i].frame_index < 0) { best = i; break; }
+    if (m->slots[i].pinned) continue;
     if (best < 0 || m->slots[i].last_use < m->slots[best].last_use) best = i;
+  }
+  if (best < 0) {
+    m->err = "frame store full: every slot holds a key-frame pinned by tf_upload_keyframe_rgb (raise tf_config.max_frames "
+             "or tf_release_frame)";
+    return -1;
   }
   FrameSlot& fsl = m->slots[best];
   if (fsl.frame_index >= 0) m->frame_to_slot.erase(fsl.frame_index);
   fsl.frame_index = frame_index;
   fsl.has_rgba = fsl.has_quality = fsl.has_rgb = false;
+  fsl.pinned = false;
   fsl.last_use = ++m->use_clock;
   m->frame_to_slot[frame_index] = best;
   return best;
@@ -371,7 +394,7 @@ int launch_integrate(tf_map* m, const GroupParams& gp, const int* n_dev, int n_h
 int build_group(tf_map* m, const tf_group_frame* frames, int n_frames, const tf_camera* cam, GroupParams& gp,
                 bool* color_flags) {
   if (n_frames < 1 || n_frames > kMaxGroupFrames) return fail(m, TF_ERR_INVALID, "group size must be 1..8");
-  make_group_consts(m->cfg.voxel_res, m->cfg.trunc, gp);
+  make_group_consts(m->cfg.voxel_res, m->cfg.trunc, m->cfg.dot3_order, gp);
   gp.n_frames = n_frames;
   for (int f = 0; f < n_frames; f++) {
     const int s = find_slot(m, frames[f].frame_index);
@@ -449,6 +472,7 @@ void tf_destroy(tf_map* m) {
   for (auto& sl : m->slots)
     if (sl.ready) cudaEventDestroy(sl.ready);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  if (m->reuse_ev) cudaEventDestroy(m->reuse_ev);
   cudaFree(m->md.table); cudaFree(m->md.pool); cudaFree(m->md.slot_id);
   cudaFree(m->md.slot_flags); cudaFree(m->md.free_stack); cudaFree(m->fs);
   cudaFree(m->cb.mask32); cudaFree(m->cb.local_off); cudaFree(m->cb.hit_items); cudaFree(m->cb.hit_count);
@@ -541,6 +565,7 @@ int tf_create(tf_map** out, const tf_config* cfg) {
   m->sm_count = prop.multiProcessorCount;
   C_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   C_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  C_OK(cudaEventCreateWithFlags(&m->reuse_ev, cudaEventDisableTiming));
   int occ = 1;
   C_OK(cudaFuncSetAttribute(integrate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)integrate_smem_bytes(kMaxGroupFrames)));
@@ -646,6 +671,12 @@ int tf_reset(tf_map* m) {
   return reset_device_state(m);
 }
 
+int tf_set_truncation(tf_map* m, const tf_truncation* t) {
+  if (!m || !t) return fail(m, TF_ERR_INVALID, "tf_set_truncation: bad argument");
+  m->cfg.trunc = *t;  // read when the next call builds its frame constants
+  return TF_OK;
+}
+
 int tf_sync(tf_map* m) {
   if (!m) return TF_ERR_INVALID;
   use_device(m);
@@ -679,7 +710,12 @@ int tf_upload_frame(tf_map* m, int32_t frame_index, const float* depth, const ui
   if (!m || !depth || frame_index < 0) return fail(m, TF_ERR_INVALID, "tf_upload_frame: bad argument");
   use_device(m);
   const int s = acquire_slot(m, frame_index);
+  if (s < 0) return TF_ERR_CAPACITY;
   FrameSlot& fsl = m->slots[s];
+  guard_overwrite(m, fsl);
+  // the planes of this upload replace the slot's contents: planes that are not passed are absent
+  // afterwards (the reference reads NULL pointers as "no colour" / quality 0, Structure/Chisel.h:218-249)
+  fsl.has_rgba = fsl.has_quality = fsl.has_rgb = false;
   const size_t nb = (size_t)m->npix * 4;
   CUDA_OK(m, cudaMemcpyAsync(fsl.depth, depth, nb, cudaMemcpyHostToDevice, m->copy_stream));
   m->counters.h2d_bytes += nb;
@@ -708,6 +744,8 @@ int tf_upload_keyframe_rgb(tf_map* m, int32_t frame_index, const uint8_t* rgb, c
   if (s < 0) return fail(m, TF_ERR_NOT_FOUND, "frame_index not in the frame store (upload depth first)");
   FrameSlot& fsl = m->slots[s];
   if (int rc = ensure_color_planes(m, fsl)) return rc;
+  guard_overwrite(m, fsl);
+  fsl.pinned = true;  // Frame::rgb stays available to the atlas / texcoords until tf_release_frame
   CUDA_OK(m, cudaMemcpyAsync(fsl.rgb, rgb, (size_t)m->npix * 3, cudaMemcpyHostToDevice, m->copy_stream));
   m->counters.h2d_bytes += (int64_t)m->npix * 3;
   if (color_valid) {
@@ -728,6 +766,7 @@ int tf_release_frame(tf_map* m, int32_t frame_index) {
   auto it = m->frame_to_slot.find(frame_index);
   if (it == m->frame_to_slot.end()) return fail(m, TF_ERR_NOT_FOUND, "frame_index not in the frame store");
   m->slots[it->second].frame_index = -1;
+  m->slots[it->second].pinned = false;
   m->frame_to_slot.erase(it);
   return TF_OK;
 }
@@ -737,7 +776,10 @@ int tf_frame_device_ptrs(tf_map* m, int32_t frame_index, int has_color, void** d
   if (!m || frame_index < 0) return fail(m, TF_ERR_INVALID, "tf_frame_device_ptrs: bad argument");
   use_device(m);
   const int s = acquire_slot(m, frame_index);
+  if (s < 0) return TF_ERR_CAPACITY;
   FrameSlot& fsl = m->slots[s];
+  guard_overwrite(m, fsl);
+  fsl.has_rgba = fsl.has_quality = fsl.has_rgb = false;
   if (has_color) {
     if (int rc = ensure_color_planes(m, fsl)) return rc;
     fsl.has_rgba = fsl.has_quality = true;
@@ -757,7 +799,7 @@ int tf_prepare(tf_map* m, int32_t frame_index, const tf_pose* pose, const tf_cam
   const int s = find_slot(m, frame_index);
   if (s < 0) return fail(m, TF_ERR_NOT_FOUND, "frame_index not in the frame store");
   CullParams cp;
-  make_cull_params(m->cfg.voxel_res, m->cfg.trunc, *pose, *cam, cp);
+  make_cull_params(m->cfg.voxel_res, m->cfg.trunc, m->cfg.dot3_order, *pose, *cam, cp);
   // pass 1: culling only, to learn the list length before anything is created
   static const GroupParams kNoFrames{};
   if (int rc = launch_cull(m, cp, kNoFrames, m->slots[s].depth, false, true)) return rc;
@@ -974,7 +1016,7 @@ static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, co
   bool color[kMaxGroupFrames];
   if (int rc = build_group(m, frames, n_frames, cam, a.gp, color)) return rc;
   const int s = find_slot(m, frames[0].frame_index);
-  make_cull_params(m->cfg.voxel_res, m->cfg.trunc, frames[0].pose, *cam, a.cp);
+  make_cull_params(m->cfg.voxel_res, m->cfg.trunc, m->cfg.dot3_order, frames[0].pose, *cam, a.cp);
   if (int rc = ensure_setup(m, n_frames)) return rc;
   HT(1);
   const bool want_lists = ids_out || new_out || upd_out || q_out;
@@ -1207,7 +1249,7 @@ int tf_integrate_batch(tf_map* m, const tf_batch_item* items, int64_t n_items, c
       p.n_frames = it.n_frames;
       if (int rc = build_group(m, fr, it.n_frames, cam, a.gp, p.color)) return rc;
       const int s = find_slot(m, fr[0].frame_index);
-      make_cull_params(m->cfg.voxel_res, m->cfg.trunc, fr[0].pose, *cam, a.cp);
+      make_cull_params(m->cfg.voxel_res, m->cfg.trunc, m->cfg.dot3_order, fr[0].pose, *cam, a.cp);
       // (an item that asks for nothing back — streaming fusion of a frame sequence — skips the
       //  ordering scan and the export; only its list length is recorded)
       const bool want_lists = it.valid_out || it.quality_out || it.n_valid_out;

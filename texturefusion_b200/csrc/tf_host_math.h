@@ -10,12 +10,9 @@
 
 namespace tfb {
 
-inline float h_dot3(float a0, float b0, float a1, float b1, float a2, float b2) {
-#ifdef TF_DOT3_LEFT_TO_RIGHT
-  return (a0 * b0 + a1 * b1) + a2 * b2;
-#else
-  return a0 * b0 + (a1 * b1 + a2 * b2);  // Eigen redux_novec_unroller<0,3>
-#endif
+// (see dot3 in tf_device.cuh)
+inline float h_dot3(int l2r, float a0, float b0, float a1, float b1, float a2, float b2) {
+  return l2r ? (a0 * b0 + a1 * b1) + a2 * b2 : a0 * b0 + (a1 * b1 + a2 * b2);
 }
 
 // tf_pose is column-major camera->world: R(i,j) = m[j*4+i]; Rt(i,j) = m[i*4+j].
@@ -29,11 +26,12 @@ inline void pose_split(const tf_pose& p, float R[9], float Rt[9], float t[3]) {
 }
 
 // GetChunkIDsObservedByCamera set-up (Structure/ChunkManager.h:398-470) + bbox constants.
-inline void make_cull_params(float res, const tf_truncation& tr, const tf_pose& pose, const tf_camera& cam,
+inline void make_cull_params(float res, const tf_truncation& tr, int l2r, const tf_pose& pose, const tf_camera& cam,
                              CullParams& cp) {
   pose_split(pose, cp.R, cp.Rt, cp.t);
+  cp.l2r = l2r;
   for (int k = 0; k < 3; k++)
-    cp.tau[k] = h_dot3(cp.Rt[k * 3 + 0], cp.t[0], cp.Rt[k * 3 + 1], cp.t[1], cp.Rt[k * 3 + 2], cp.t[2]);
+    cp.tau[k] = h_dot3(l2r, cp.Rt[k * 3 + 0], cp.t[0], cp.Rt[k * 3 + 1], cp.t[1], cp.Rt[k * 3 + 2], cp.t[2]);
   for (int k = 0; k < 3; k++)
     for (int i = 0; i < 3; i++) cp.r[k][i] = cp.Rt[i * 3 + k] * 8.0f * res;
   float diag = 8 * res / 2;
@@ -51,7 +49,7 @@ inline void make_cull_params(float res, const tf_truncation& tr, const tf_pose& 
         const float c0 = (float)(x * 8), c1 = (float)(y * 8), c2 = (float)(z * 8);
         const int idx = x + y * 2 + z * 4;
         for (int k = 0; k < 3; k++) {
-          const float rc = h_dot3(cp.Rt[k * 3 + 0], c0, cp.Rt[k * 3 + 1], c1, cp.Rt[k * 3 + 2], c2);
+          const float rc = h_dot3(l2r, cp.Rt[k * 3 + 0], c0, cp.Rt[k * 3 + 1], c1, cp.Rt[k * 3 + 2], c2);
           cp.off_c[idx][k] = rc * res * (float)step + half;
           cp.off_f[idx][k] = rc * res * 1.0f + half;
         }
@@ -87,8 +85,9 @@ inline void make_frame_dev(const tf_pose& pose, const tf_camera& cam, int flag, 
   f.depth = depth, f.rgba = rgba, f.quality = quality;
 }
 
-inline void make_group_consts(float res, const tf_truncation& tr, GroupParams& gp) {
+inline void make_group_consts(float res, const tf_truncation& tr, int l2r, GroupParams& gp) {
   gp.res = res;
+  gp.l2r = l2r;
   gp.half = res * 0.5f;
   // `sqrt(3.0f) * resolution` binds to ::sqrt(double): double product rounded to float.
   // (spelled out: in a .cu file sqrt(float) would resolve to CUDA's float overload)
