@@ -46,13 +46,17 @@ def load_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one captured integrate_kernel launch
-    (ncu --set full; profiles/r1_integrate_traffic.json), or None when no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r1_integrate_traffic.json")
+def load_traffic(steps, warmup):
+    """dram__bytes_read.sum + dram__bytes_write.sum per integrate_kernel launch from the ncu capture
+    of THIS command line (profiles/r2_integrate_traffic.json records the --steps/--warmup it was taken
+    with and the launches it averaged); None when no capture matches the current arguments — a
+    figure from a different workload would not be comparable with `achieved`."""
+    p = os.path.join(ROOT, "profiles", "r2_integrate_traffic.json")
     try:
         d = json.load(open(p))
-        return float(d["dram_bytes_per_launch"]), d["note"]
+        if int(d["steps"]) == steps and int(d["warmup"]) == warmup:
+            return float(d["dram_bytes_per_launch"]), d["note"]
+        return None, f"capture in profiles/ is for --steps {d['steps']} --warmup {d['warmup']}, not this run"
     except Exception:
         return None, "no ncu capture committed"
 
@@ -106,10 +110,16 @@ def make_data(n_frames, device):
     return seq, time.time() - t0
 
 
-def run_cpu_reference(seq, res, steps, warmup, budget_s, threads):
-    """The reference's CPU path (oracle port): Prepare + Integrate + Finalize per frame."""
+def cpu_impl():
+    """("ref", "reference") when oracle/_ref — the reference's own sources — is built, else the restated port."""
+    from oracle import have_ref
+    return ("ref", "reference") if have_ref() else ("port", "port")
+
+
+def run_cpu_reference(seq, res, steps, warmup, budget_s, threads, want_hash=False):
+    """The reference's CPU path: Prepare + Integrate + Finalize per frame (IntegrateFrame shape)."""
     from oracle import OracleMap
-    o = OracleMap(res, threads=threads)
+    o = OracleMap(res, threads=threads, impl=cpu_impl()[0])
     frames = seq.frames
     rgba = {fr.index: fr.rgba() for fr in frames if fr.is_keyframe}
     k = 0
@@ -129,8 +139,12 @@ def run_cpu_reference(seq, res, steps, warmup, budget_s, threads):
         k += 1
         if t_total > budget_s:
             break
-    return {"fps": done / t_total, "frames": done, "seconds": t_total, "voxel_updates_per_s": vox / t_total,
-            "cores": o.threads_used}
+    out = {"fps": done / t_total, "frames": done, "seconds": t_total, "voxel_updates_per_s": vox / t_total,
+           "cores": o.threads_used}
+    if want_hash:
+        from texturefusion_b200.maphash import map_hash
+        out["map_chunks"], out["map_hash"] = map_hash(o)
+    return out
 
 
 def flush_l2(torch, buf):
@@ -147,7 +161,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.warmup = max(args.warmup, 3)  # both arms: they fuse the same frames
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -158,6 +172,8 @@ def main():
     n_need = min(SEQ_FRAMES, args.steps + args.warmup)
     config = {"workload": "configs[1]: synthetic 640x480 room sequence (300 poses, key-frame every 10th frame with "
                           "colour+quality, others depth-only), TSDF + voxel colour fusion, Prepare+Integrate+Finalize per frame",
+              "frames_fused": f"frames 0..{n_need - 1} of the sequence into an empty map: {args.warmup} warm-up + {args.steps} "
+                              "timed (past frame 299 the sequence repeats)",
               "voxel_res_m": args.res, "frames_in_sequence": SEQ_FRAMES, "image": "640x480",
               "l2": "flushed between timed steps (512 MiB write), flush excluded from the timed region",
               "parallelism": f"chunk-sharded x{args.gpus}" if args.gpus > 1 else "single GPU"}
@@ -167,17 +183,21 @@ def main():
         if rank != 0:
             return
         seq, _ = make_data(n_need, "cuda" if have_cuda else "cpu")
-        steps = min(args.steps, 120)  # bounded sample: ~10-30 s of CPU work
-        r = run_cpu_reference(seq, args.res, steps, min(args.warmup, 3), 60.0, threads=0)
+        # the same frames as our arm (same warm-up, same steps, empty map); bounded by a time budget only
+        r = run_cpu_reference(seq, args.res, args.steps, args.warmup, 120.0, threads=0, want_hash=True)
+        kind = cpu_impl()[1]
+        what = ("the reference's own sources (oracle/_ref: ProjectionIntegrator.cpp + ChunkManager.{h,cpp} built against the "
+                "Eigen stand-in)" if kind == "reference" else "oracle port")
         line = {"impl": "reference", "metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus,
-                "steps": r["frames"], "warmup": min(args.warmup, 3), "ms_per_step": 1e3 / r["fps"],
+                "steps": r["frames"], "warmup": args.warmup, "ms_per_step": 1e3 / r["fps"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config,
-                "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
-                                 "sample": f"first {r['frames']} frames of the workload after {min(args.warmup, 3)} warm-up frames, "
-                                           "oracle port with the reference's parallel_for policy"},
+                "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": kind,
+                                 "sample": f"{r['frames']} frames of the workload after {args.warmup} warm-up frames, "
+                                           f"{what}, the reference's parallel_for policy (hardware_concurrency-2 threads)"},
                 "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "voxel_updates_per_s": r["voxel_updates_per_s"]}
+                "voxel_updates_per_s": r["voxel_updates_per_s"],
+                "map_chunks": r["map_chunks"], "map_hash": f"{r['map_hash']:016x}"}
         print(json.dumps(line))
         return
 
@@ -295,9 +315,12 @@ def main():
     stage_us = {k: 1e3 * v / args.steps for k, v in m.stage_times().items()}
     m.close()
     achieved = (k_bytes / 1e9) / (k_ms * 1e-3) if k_ms > 0 else 0.0
-    traffic, traffic_note = load_traffic()
+    traffic, traffic_note = load_traffic(args.steps, args.warmup)
     roofline = {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                "frac": achieved / peak_gbs, "traffic": traffic, "traffic_note": traffic_note,
+                # real DRAM bytes / kernel time / peak (only when the capture is of this command)
+                "frac_dram": (traffic / 1e9) / (1e-3 * k_ms / max(k_n, 1)) / peak_gbs if traffic and k_ms > 0 else None,
+                "peak_source": peak_src,
                 "launches": k_n, "avg_launch_us": 1e3 * k_ms / max(k_n, 1),
                 "algorithmic_bytes_per_launch": k_bytes / max(k_n, 1),
                 "kernel_share_of_step": k_ms / dev_ms if dev_ms > 0 else None}
@@ -309,79 +332,19 @@ def main():
     # write it: tf_upload_frame(i+1) is issued before tf_integrate_frame(i), so the copy of the next
     # frame overlaps the kernels of the current one; tf_wait_upload at the end of the step makes sure that
     # copy has finished inside the timed region.
+    from texturefusion_b200.streaming import FrameStreamer
     m = capi.Map(args.res, device=local_rank, n_ranks=world, rank=rank, max_frames=32, max_chunks=1 << 19)
-    pin_d = [capi.PinnedBuffer((cam.height, cam.width), np.float32) for _ in range(nf)]
-    pin_c, pin_q = {}, {}
-    for i, fr in enumerate(frames):
-        pin_d[i].array[...] = fr.depth
-        if fr.is_keyframe:
-            pin_c[i] = capi.PinnedBuffer((cam.height, cam.width, 4), np.uint8)
-            pin_c[i].array[...] = rgba[fr.index]
-            pin_q[i] = capi.PinnedBuffer((cam.height, cam.width), np.float32)
-            pin_q[i].array[...] = fr.quality
-    cap = 1 << 16
-    out_ids = capi.PinnedBuffer((cap, 3), np.int32)
-    out_new = capi.PinnedBuffer((cap,), np.uint8)
-    out_upd = capi.PinnedBuffer((cap,), np.uint8)
-    out_q = capi.PinnedBuffer((cap,), np.float32)
-    L = m.L
-    vp = C.c_void_p
-
-    def upload(i):
-        fr = frames[i]
-        rc = L.tf_upload_frame(m.h, fr.index, vp(pin_d[i].ptr), vp(pin_c[i].ptr) if fr.is_keyframe else None,
-                               vp(pin_q[i].ptr) if fr.is_keyframe else None)
-        assert rc == 0, L.tf_last_error(m.h)
-
-    def fuse(i):
-        fr = frames[i]
-        rc = L.tf_integrate_frame(m.h, fr.index, int(fr.is_keyframe), C.byref(poses[i]), C.byref(camc), C.byref(st),
-                                  vp(out_ids.ptr), vp(out_new.ptr), vp(out_upd.ptr), vp(out_q.ptr), cap)
-        assert rc == 0, L.tf_last_error(m.h)
-        return st.n_chunks
-
-    # Multi-GPU: rank 0 ingests frame i+1 (H2D on the map's copy stream) and the planes are broadcast
-    # over NVLink into every rank's frame store ON THAT STREAM, i.e. behind the copy and next to the
-    # kernels of frame i; the compute stream waits for the broadcast's event before frame i+1.
-    bcast_ready = {}
-    if dist is not None:
-        ext_copy = torch.cuda.ExternalStream(m.copy_stream(), device=dev)
-        ext_comp = torch.cuda.ExternalStream(m.stream(), device=dev)
-
-    def stage_broadcast(i):
-        fr = frames[i]
-        d_ptr, c_ptr, q_ptr = m.frame_device_ptrs(fr.index, fr.is_keyframe)
-        if rank == 0:
-            upload(i)
-        with torch.cuda.stream(ext_copy):
-            for ptr in [d_ptr] + ([c_ptr, q_ptr] if fr.is_keyframe else []):
-                dist.broadcast(dev_tensor(torch, ptr, cam.height * cam.width, local_rank), src=0)
-            ev = torch.cuda.Event()
-            ev.record(ext_copy)
-        bcast_ready[i] = ev
-
-    def e2e_step(i):
-        if dist is not None:
-            j = (i + 1) % nf
-            stage_broadcast(j)                      # in flight during this frame's kernels
-            ext_comp.wait_event(bcast_ready.pop(i))  # (device-side wait: frame i has arrived)
-            n = fuse(i)
-            bcast_ready[j].synchronize()             # ... and finished inside this timed step
-            return n
-        j = (i + 1) % nf
-        upload(j)  # next frame's copy, in flight during this frame's kernels
-        n = fuse(i)
-        rc = L.tf_wait_upload(m.h, frames[j].index)  # ... and finished inside this timed step
-        assert rc == 0
-        return n
+    if dist is not None:  # NCCL communicator of the library itself (the id travels through torch.distributed, once)
+        m.comm_init(capi.share_unique_id(dist, dev))
+    # Multi-GPU: rank 0 ingests frame i+1 (H2D on the map's copy stream) and tf_broadcast_frame moves its
+    # planes over NVLink into every rank's frame store with one ncclBroadcast ON THAT STREAM, i.e. behind
+    # the copy and next to the kernels of frame i; the compute stream waits for the slot's event.
+    fs = FrameStreamer(m, frames, cam, rank=rank, world=world, cap=1 << 16)
+    e2e_step = fs.step
 
     k = 0
-    if dist is None:
-        upload(0)
-        m.sync()
-    else:
-        stage_broadcast(0)
-        torch.cuda.synchronize()
+    fs.stage(0)
+    m.sync()
     for _ in range(args.warmup):
         e2e_step(k % nf)
         k += 1
@@ -406,8 +369,19 @@ def main():
            "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / args.steps,
            "ms_per_step": 1e3 * e2e_s / args.steps, "median_ms_per_step": 1e3 * float(np.median(step_s)),
            "mode": ("double buffered: upload(i+1) | fuse(i) | wait_upload(i+1), host buffers page-locked" if dist is None else
-                    "double buffered: rank 0 uploads frame i+1 and all ranks broadcast it (NCCL) on the copy stream | "
-                    "fuse(i) on every rank's shard | wait for the broadcast")}
+                    "double buffered: rank 0 uploads frame i+1, tf_broadcast_frame (one ncclBroadcast inside the library, on the "
+                    "copy stream) | fuse(i) on every rank's shard | tf_wait_upload(i+1); no Python between the C calls")}
+    # The map the e2e pass built (frames 0..warmup+steps-1 from empty), as a shard-independent checksum:
+    # the same at every N and in the reference arm's line if and only if the fused maps are identical.
+    from texturefusion_b200.maphash import map_hash
+    m.sync()
+    map_chunks, mh = map_hash(m)
+    if dist is not None:
+        parts = torch.tensor([map_chunks, mh & 0xffffffff, mh >> 32], dtype=torch.int64, device=dev)
+        allp = [torch.zeros_like(parts) for _ in range(world)]
+        dist.all_gather(allp, parts)
+        map_chunks = int(sum(int(p[0]) for p in allp))
+        mh = sum((int(p[2]) << 32) | int(p[1]) for p in allp) & ((1 << 64) - 1)
     m.close()
 
     if rank != 0:
@@ -422,37 +396,28 @@ def main():
     if args.gpus == 1 and not args.no_cpu_baseline:
         runs, spent = [], 0.0
         while spent < args.cpu_budget and len(runs) < 8:
-            r = run_cpu_reference(seq, args.res, min(args.steps, nf), 2, args.cpu_budget, threads=0)
+            r = run_cpu_reference(seq, args.res, min(args.steps, nf), args.warmup, args.cpu_budget, threads=0)
             runs.append(r)
             spent += r["seconds"]
         fps = sum(r["frames"] for r in runs) / sum(r["seconds"] for r in runs)
         vps = sum(r["voxel_updates_per_s"] * r["seconds"] for r in runs) / sum(r["seconds"] for r in runs)
-        cpu_baseline = {"value": fps, "unit": "frames/s", "cores": runs[0]["cores"], "kind": "port",
-                        "sample": f"{len(runs)} x the first {runs[0]['frames']} frames of the same workload from an empty map "
-                                  f"({spent:.1f} s of CPU work in total), oracle port, reference parallel_for policy "
-                                  "(hardware_concurrency-2 threads, >=1000 chunks per group)",
+        cpu_baseline = {"value": fps, "unit": "frames/s", "cores": runs[0]["cores"], "kind": cpu_impl()[1],
+                        "sample": f"{len(runs)} x {runs[0]['frames']} frames of the same workload after {args.warmup} warm-up frames, "
+                                  f"from an empty map ({spent:.1f} s of CPU work in total), "
+                                  + ("the reference's own sources (oracle/_ref)" if cpu_impl()[1] == "reference" else "oracle port")
+                                  + ", reference parallel_for policy (hardware_concurrency-2 threads, >=1000 chunks per group)",
                         "voxel_updates_per_s": vps}
 
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "voxel_updates_per_s": vox / (dev_ms * 1e-3), "chunks_per_frame": chunks / args.steps,
-            "live_chunks": live_chunks, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "live_chunks": live_chunks, "map_chunks": map_chunks, "map_hash": f"{mh:016x}", "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "data_gen_s": gen_s,
             "stage_us_per_frame": stage_us}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
-
-
-class _DevPtr:
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-
-
-def dev_tensor(torch, ptr, n_words, device):
-    """A torch view over a raw device plane of the frame store (for the NCCL broadcast)."""
-    return torch.as_tensor(_DevPtr(ptr, n_words), device=f"cuda:{device}")
 
 
 if __name__ == "__main__":

@@ -133,6 +133,21 @@ int tf_release_frame(tf_map* m, int32_t frame_index);
 int tf_frame_device_ptrs(tf_map* m, int32_t frame_index, int has_color, void** depth,
                          void** rgba, void** quality);
 
+/* ---- multi-GPU: frame broadcast (no reference counterpart) --------------------
+ * One process per GPU, each with a tf_map created with the same n_ranks and its own rank; chunks
+ * are owned by rank (tf_config.n_ranks / rank), so the only per-frame exchange is the frame itself.
+ * tf_comm_unique_id: ncclGetUniqueId on one rank; the caller hands the 128 bytes to the others
+ * (MPI, torch.distributed, a file, ...).  tf_comm_init: ncclCommInitRank on every rank (collective).
+ * NCCL is loaded at run time (libnccl.so.2; TEXFUSION_B200_NCCL overrides the path).
+ * tf_broadcast_frame (collective, asynchronous): the root has uploaded frame_index
+ * (tf_upload_frame); its depth (+ rgba + quality when has_color) planes land in every other rank's
+ * frame store with ONE ncclBroadcast queued on the upload stream, i.e. behind the root's own
+ * host-to-device copy and next to the kernels of the frame being fused.  Consumers of the frame wait
+ * for it on the device; tf_wait_upload waits on the host. */
+int tf_comm_unique_id(uint8_t id_out[128]);
+int tf_comm_init(tf_map* m, const uint8_t id[128]);
+int tf_broadcast_frame(tf_map* m, int32_t frame_index, int has_color, int root);
+
 /* ---- per-frame hot path -------------------------------------------------------------- */
 
 /* Chisel::PrepareIntersectChunks (Structure/Chisel.h:103-140): depth bbox

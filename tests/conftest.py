@@ -33,7 +33,8 @@ def pytest_collection_modifyitems(config, items):
 def _built():
     """Make sure both shared libraries exist (the driver normally runs build() first)."""
     from texturefusion_b200.build import build_library
-    from oracle import build_oracle
+    from oracle import build_oracle, build_ref
     build_oracle()
+    build_ref()  # no-op without /root/reference (the GPU box uses the prebuilt oracle/_ref)
     build_library()
     yield

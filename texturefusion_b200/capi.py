@@ -20,6 +20,7 @@ DEFAULT_TRUNC = (0.0019, 0.00152, 0.001504, 6.0, 1.0)
 EXPORTS = [
     "tf_create", "tf_destroy", "tf_last_error", "tf_reset", "tf_set_truncation", "tf_host_alloc", "tf_host_free",
     "tf_upload_frame", "tf_upload_keyframe_rgb", "tf_release_frame", "tf_frame_device_ptrs",
+    "tf_comm_unique_id", "tf_comm_init", "tf_broadcast_frame",
     "tf_prepare", "tf_integrate", "tf_integrate_group", "tf_remove_chunks", "tf_integrate_frame",
     "tf_integrate_batch", "tf_has_chunk", "tf_chunk_count", "tf_list_chunks", "tf_download_chunks",
     "tf_atlas_alloc_slot", "tf_atlas_update", "tf_atlas_download", "tf_atlas_patch_size", "tf_patch_texcoords", "tf_sync", "tf_wait_upload",
@@ -109,6 +110,9 @@ def load() -> C.CDLL:
     L.tf_upload_keyframe_rgb.argtypes = [vp, C.c_int32, vp, vp]
     L.tf_release_frame.argtypes = [vp, C.c_int32]
     L.tf_frame_device_ptrs.argtypes = [vp, C.c_int32, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.tf_comm_unique_id.argtypes = [vp]
+    L.tf_comm_init.argtypes = [vp, vp]
+    L.tf_broadcast_frame.argtypes = [vp, C.c_int32, C.c_int, C.c_int]
     L.tf_prepare.argtypes = [vp, C.c_int32, C.POINTER(Pose), C.POINTER(Camera), vp, vp, i64, C.POINTER(i64)]
     L.tf_integrate.argtypes = [vp, C.c_int32, C.c_int, C.POINTER(Pose), C.POINTER(Camera), vp, i64, C.c_int, vp, vp]
     L.tf_integrate_group.argtypes = [vp, C.POINTER(GroupFrame), C.c_int32, C.POINTER(Camera), vp, i64, vp, vp]
@@ -139,6 +143,26 @@ def load() -> C.CDLL:
     L.tf_debug_project.argtypes = [vp, vp, vp, i64, C.c_float, C.c_float, vp, vp, vp]
     _LIB = L
     return L
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (call on one rank, share the bytes with the others)."""
+    L = load()
+    buf = (C.c_uint8 * 128)()
+    rc = L.tf_comm_unique_id(buf)
+    if rc != TF_OK:
+        raise TexFusionError(rc, L.tf_last_error(None).decode())
+    return bytes(buf)
+
+
+def share_unique_id(dist, device) -> bytes:
+    """Rank 0's NCCL id handed to every rank through an initialised torch.distributed group."""
+    import torch
+    t = torch.zeros(128, dtype=torch.uint8, device=device)
+    if dist.get_rank() == 0:
+        t = torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8).to(device)
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().numpy().tobytes())
 
 
 class TexFusionError(RuntimeError):
@@ -250,6 +274,18 @@ class Map:
         d, c, q = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._check(self.L.tf_frame_device_ptrs(self.h, frame_index, int(has_color), C.byref(d), C.byref(c), C.byref(q)))
         return d.value, c.value, q.value
+
+    # multi-GPU ---------------------------------------------------------------------------
+    def comm_init(self, unique_id: bytes):
+        """ncclCommInitRank with the id from comm_unique_id() of one rank (collective)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self.L.tf_comm_init(self.h, buf))
+
+    def broadcast_frame(self, frame_index, has_color, root=0):
+        self._check(self.L.tf_broadcast_frame(self.h, frame_index, int(has_color), root))
+
+    def wait_upload(self, frame_index):
+        self._check(self.L.tf_wait_upload(self.h, frame_index))
 
     # hot path ----------------------------------------------------------------------------
     def prepare(self, frame_index, pose, cam, cap=None):

@@ -9,6 +9,7 @@
 #include <chrono>
 #endif
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -44,6 +45,45 @@ struct FrameSlot {
   bool pinned = false;          // key-frame rgb kept for the atlas: not evictable until tf_release_frame
 };
 
+// ---- NCCL, bound at run time --------------------------------------------------------------------
+// The one per-frame collective of the sharded path is the frame broadcast.  The library does not
+// link against NCCL (single-GPU users need none): tf_comm_init dlopens libnccl.so.2 — in a process
+// that already carries one (e.g. the copy bundled with PyTorch) that is the copy it gets — and
+// binds the five entry points it uses.  Types restated from nccl.h (ABI-stable since NCCL 2.0).
+typedef struct ncclComm* nccl_comm_t;
+struct nccl_unique_id { char internal[128]; };
+constexpr int kNcclUint8 = 1;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(nccl_unique_id*) = nullptr;
+  int (*CommInitRank)(nccl_comm_t*, int, nccl_unique_id, int) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string err;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  if (api.lib || !api.err.empty()) return &api;
+  const char* names[] = {getenv("TEXFUSION_B200_NCCL"), "libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    if (!n) continue;
+    api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) { api.err = std::string("cannot load NCCL: ") + dlerror(); return &api; }
+  api.GetUniqueId = (int (*)(nccl_unique_id*))dlsym(api.lib, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(nccl_comm_t*, int, nccl_unique_id, int))dlsym(api.lib, "ncclCommInitRank");
+  api.CommDestroy = (int (*)(nccl_comm_t))dlsym(api.lib, "ncclCommDestroy");
+  api.Broadcast = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(api.lib, "ncclBroadcast");
+  api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Broadcast || !api.GetErrorString) {
+    api.err = "libnccl lacks an expected symbol";
+    api.lib = nullptr;
+  }
+  return &api;
+}
+
 struct EventPair {
   cudaEvent_t a, b;
   double bytes;
@@ -71,8 +111,9 @@ struct tf_map {
   cudaStream_t copy_stream = nullptr;  // frame uploads: the next frame's H2D copy overlaps the current frame's kernels
   cudaEvent_t reuse_ev = nullptr;      // orders an overwriting upload behind the kernels that read the slot
   std::string err;
-  float* slab_depth = nullptr;          // frame store: depth planes of all slots
-  unsigned char* slab_color = nullptr;  // rgba | quality | rgb | valid planes of all slots
+  unsigned char* slab = nullptr;        // frame store: per slot [depth | rgba | quality | rgb | valid], contiguous so
+  size_t slot_stride = 0;               // that one broadcast moves depth (+ rgba + quality) of a frame
+  nccl_comm_t comm = nullptr;           // tf_comm_init
   int grid_bbox = 0;
   int sm_count = 0, grid = 0, grid_cull = 0, grid_integrate = 0, grid_integrate_c = 0;
 
@@ -468,6 +509,7 @@ void tf_destroy(tf_map* m) {
   cudaSetDevice(m->cfg.device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
+  if (m->comm) nccl_api()->CommDestroy(m->comm);
   destroy_graphs(m);
   for (auto& sl : m->slots)
     if (sl.ready) cudaEventDestroy(sl.ready);
@@ -482,8 +524,7 @@ void tf_destroy(tf_map* m) {
   cudaFree(m->count_d); cudaFree(m->atlas); cudaFree(m->patch_d);
   cudaFreeHost(m->res_h); cudaFreeHost(m->out_ids_h); cudaFreeHost(m->out_new_h); cudaFreeHost(m->out_upd_h);
   cudaFreeHost(m->out_q_h); cudaFreeHost(m->upd_stage_h); cudaFreeHost(m->q_stage_h);
-  cudaFree(m->slab_depth);
-  cudaFree(m->slab_color);
+  cudaFree(m->slab);
   cudaFree(m->st_ids); cudaFree(m->st_new); cudaFree(m->st_upd); cudaFree(m->st_q);
   cudaFreeHost(m->arena_ids); cudaFreeHost(m->arena_q); cudaFreeHost(m->arena_upd); cudaFreeHost(m->batch_rec);
   cudaFreeHost(m->ids_stage);
@@ -635,24 +676,23 @@ int tf_create(tf_map** out, const tf_config* cfg) {
   C_OK(cudaHostGetDevicePointer((void**)&m->out_q_d, m->out_q_h, 0));
 
   const int max_frames = cfg->max_frames > 0 ? cfg->max_frames : 32;
-  // The frame store is allocated up front as two slabs (16 B per pixel and slot with colour):
-  // cudaMalloc in the per-frame path would stall the stream for hundreds of microseconds.
+  // The frame store is allocated up front as one slab (4 B per pixel and slot, 16 B with colour):
+  // cudaMalloc in the per-frame path would stall the stream for hundreds of microseconds.  A slot
+  // is [depth | rgba | quality | rgb | valid]: the planes a broadcast moves are contiguous.
   m->slots.resize(max_frames);
-  const size_t depth_stride = ((size_t)m->npix + 3) & ~(size_t)3;  // keeps every plane 16-byte aligned (float4 loads)
-  C_OK(dmalloc(&m->slab_depth, depth_stride * max_frames));
+  const size_t plane = (((size_t)m->npix * 4) + 15) & ~(size_t)15;  // keeps every plane 16-byte aligned (float4 loads)
+  m->slot_stride = cfg->use_color ? plane * 3 + (((size_t)m->npix * 4 + 15) & ~(size_t)15) : plane;
+  C_OK(cudaMalloc((void**)&m->slab, m->slot_stride * max_frames));
   for (int i = 0; i < max_frames; i++) {
-    m->slots[i].depth = m->slab_depth + (size_t)i * depth_stride;
-    C_OK(cudaEventCreateWithFlags(&m->slots[i].ready, cudaEventDisableTiming));
-  }
-  if (cfg->use_color) {
-    C_OK(cudaMalloc((void**)&m->slab_color, (size_t)m->npix * 12 * max_frames));
-    for (int i = 0; i < max_frames; i++) {
-      unsigned char* base = m->slab_color + (size_t)i * m->npix * 12;
-      m->slots[i].rgba = reinterpret_cast<uchar4*>(base);
-      m->slots[i].quality = reinterpret_cast<float*>(base + (size_t)m->npix * 4);
-      m->slots[i].rgb = base + (size_t)m->npix * 8;
-      m->slots[i].valid = base + (size_t)m->npix * 11;
+    unsigned char* base = m->slab + (size_t)i * m->slot_stride;
+    m->slots[i].depth = reinterpret_cast<float*>(base);
+    if (cfg->use_color) {
+      m->slots[i].rgba = reinterpret_cast<uchar4*>(base + plane);
+      m->slots[i].quality = reinterpret_cast<float*>(base + 2 * plane);
+      m->slots[i].rgb = base + 3 * plane;
+      m->slots[i].valid = base + 3 * plane + (size_t)m->npix * 3;
     }
+    C_OK(cudaEventCreateWithFlags(&m->slots[i].ready, cudaEventDisableTiming));
   }
 
   // Atlas::SetResolution (Structure/Atlas.h:62-65)
@@ -787,6 +827,65 @@ int tf_frame_device_ptrs(tf_map* m, int32_t frame_index, int has_color, void** d
   if (depth) *depth = fsl.depth;
   if (rgba) *rgba = has_color ? (void*)fsl.rgba : nullptr;
   if (quality) *quality = has_color ? (void*)fsl.quality : nullptr;
+  return TF_OK;
+}
+
+// ---- multi-GPU: the frame broadcast --------------------------------------------------------------
+
+int tf_comm_unique_id(uint8_t* id_out) {
+  if (!id_out) return TF_ERR_INVALID;
+  NcclApi* n = nccl_api();
+  if (!n->lib) { g_create_error = n->err; return TF_ERR_CUDA; }
+  nccl_unique_id id;
+  const int rc = n->GetUniqueId(&id);
+  if (rc != 0) { g_create_error = std::string("ncclGetUniqueId: ") + n->GetErrorString(rc); return TF_ERR_CUDA; }
+  memcpy(id_out, id.internal, sizeof(id.internal));
+  return TF_OK;
+}
+
+int tf_comm_init(tf_map* m, const uint8_t* id128) {
+  if (!m || !id128) return fail(m, TF_ERR_INVALID, "tf_comm_init: bad argument");
+  if (m->comm) return fail(m, TF_ERR_INVALID, "tf_comm_init: communicator already initialised");
+  use_device(m);
+  NcclApi* n = nccl_api();
+  if (!n->lib) return fail(m, TF_ERR_CUDA, n->err);
+  nccl_unique_id id;
+  memcpy(id.internal, id128, sizeof(id.internal));
+  const int rc = n->CommInitRank(&m->comm, m->cfg.n_ranks, id, m->cfg.rank);
+  if (rc != 0) { m->comm = nullptr; return fail(m, TF_ERR_CUDA, std::string("ncclCommInitRank: ") + n->GetErrorString(rc)); }
+  return TF_OK;
+}
+
+int tf_broadcast_frame(tf_map* m, int32_t frame_index, int has_color, int root) {
+  if (!m || frame_index < 0 || root < 0 || root >= m->cfg.n_ranks) return fail(m, TF_ERR_INVALID, "tf_broadcast_frame: bad argument");
+  if (!m->comm) return fail(m, TF_ERR_INVALID, "tf_broadcast_frame: call tf_comm_init first");
+  use_device(m);
+  int s;
+  if (m->cfg.rank == root) {  // the ingest rank: the frame was uploaded (its copy is queued on the copy stream)
+    s = find_slot(m, frame_index, false);
+    if (s < 0) return fail(m, TF_ERR_NOT_FOUND, "tf_broadcast_frame: the root has not uploaded this frame");
+    if (has_color && !(m->slots[s].has_rgba && m->slots[s].has_quality))
+      return fail(m, TF_ERR_NOT_FOUND, "tf_broadcast_frame: the root's frame has no colour + quality planes");
+  } else {
+    s = acquire_slot(m, frame_index);
+    if (s < 0) return TF_ERR_CAPACITY;
+    guard_overwrite(m, m->slots[s]);
+    m->slots[s].has_rgba = m->slots[s].has_quality = m->slots[s].has_rgb = false;
+  }
+  FrameSlot& fsl = m->slots[s];
+  if (has_color) {
+    if (int rc = ensure_color_planes(m, fsl)) return rc;
+    fsl.has_rgba = fsl.has_quality = true;
+  }
+  // depth | rgba | quality are contiguous in the slot: one collective per frame, on the copy stream
+  // (behind the root's H2D copy, next to the kernels of the frame being fused)
+  const size_t plane = (((size_t)m->npix * 4) + 15) & ~(size_t)15;
+  const size_t bytes = has_color ? 3 * plane : (size_t)m->npix * 4;
+  const int rc = nccl_api()->Broadcast(fsl.depth, fsl.depth, bytes, kNcclUint8, root, m->comm, m->copy_stream);
+  if (rc != 0) return fail(m, TF_ERR_CUDA, std::string("ncclBroadcast: ") + nccl_api()->GetErrorString(rc));
+  CUDA_OK(m, cudaEventRecord(fsl.ready, m->copy_stream));
+  fsl.pending = true;
+  m->counters.kernel_launches++;  // (NCCL's broadcast kernel)
   return TF_OK;
 }
 

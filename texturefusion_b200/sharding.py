@@ -1,8 +1,8 @@
 """Chunk ownership and per-rank result merging for the chunk-sharded multi-GPU path.
 
-One process per GPU; rank r owns the chunks whose 4x4x4 block hashes to r with the
-reference's ChunkHasher (Structure/ChunkManager.h:44-53).  The device applies the same
-function inside cull_fine_kernel (tf_device.cuh: owner_of); this module is the host-side
+One process per GPU; rank r owns the chunks whose 8x8x8-chunk block hashes to r with the
+reference's ChunkHasher (Structure/ChunkManager.h:44-53), folded to 32 bits.  The device applies
+the same function inside cull_kernel (tf_device.cuh: owner_of); this module is the host-side
 mirror used to route host-provided chunk lists and to merge per-rank results back into the
 reference's traversal order.  There is no per-frame collective besides the frame broadcast.
 """
@@ -11,16 +11,19 @@ from __future__ import annotations
 import numpy as np
 
 _P1, _P2, _P3 = 73856093, 19349663, 83492791
+OWNER_SHIFT = 3  # == kOwnerShift in csrc/tf_device.cuh
 
 
 def owner_of(ids, n_ranks: int) -> np.ndarray:
     """Rank owning each chunk id (N x 3 int32)."""
     ids = np.asarray(ids, np.int64).reshape(-1, 3)
-    b = ids >> 2  # floor(id / 4): the coarse block the chunk lies in
+    b = ids >> OWNER_SHIFT  # floor(id / 8): the owner block the chunk lies in
     # two's complement wrap-around of size_t arithmetic, as the device computes it
-    h = (b[:, 0].astype(np.uint64) * np.uint64(_P1)) ^ (b[:, 1].astype(np.uint64) * np.uint64(_P2)) ^ \
-        (b[:, 2].astype(np.uint64) * np.uint64(_P3))
-    return (h % np.uint64(n_ranks)).astype(np.int32)
+    with np.errstate(over="ignore"):
+        h = (b[:, 0].astype(np.uint64) * np.uint64(_P1)) ^ (b[:, 1].astype(np.uint64) * np.uint64(_P2)) ^ \
+            (b[:, 2].astype(np.uint64) * np.uint64(_P3))
+    h32 = (h & np.uint64(0xffffffff)) ^ (h >> np.uint64(32))
+    return (h32 % np.uint64(n_ranks)).astype(np.int32)
 
 
 def split_by_owner(ids, n_ranks: int):

@@ -1,0 +1,92 @@
+"""The streaming loop of the fusion path as a caller writes it against the C ABI — shared by
+bench.py's end-to-end leg and the multi-process parity test, so that what is timed is what is tested.
+
+Single GPU:   upload(i+1) | fuse(i) | wait_upload(i+1)            (double buffered, page-locked sources)
+N GPUs:       rank 0 uploads frame i+1; every rank calls tf_broadcast_frame(i+1) — ONE ncclBroadcast
+              inside the library, queued on the upload stream behind the copy —; every rank fuses
+              frame i into its shard of the chunks; tf_wait_upload(i+1) closes the step.
+All arguments are marshalled once; a step is three C calls and no Python glue in between.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class FrameStreamer:
+    def __init__(self, m: capi.Map, frames, cam, *, rank=0, world=1, cap=1 << 16, want_lists=True):
+        self.m, self.frames, self.cam, self.rank, self.world = m, frames, cam, rank, world
+        self.L = m.L
+        self.nf = len(frames)
+        self.camc = capi.make_camera(cam)
+        self.poses = [capi.make_pose(fr.pose) for fr in frames]
+        self.st = capi.FrameStats()
+        self.cap = cap
+        self.want_lists = want_lists
+        self.pin_d, self.pin_c, self.pin_q = {}, {}, {}
+        if rank == 0:  # the ingest rank holds the frames in page-locked host memory
+            for i, fr in enumerate(frames):
+                self.pin_d[i] = capi.PinnedBuffer((cam.height, cam.width), np.float32)
+                self.pin_d[i].array[...] = fr.depth
+                if fr.is_keyframe:
+                    self.pin_c[i] = capi.PinnedBuffer((cam.height, cam.width, 4), np.uint8)
+                    self.pin_c[i].array[...] = fr.rgba()
+                    self.pin_q[i] = capi.PinnedBuffer((cam.height, cam.width), np.float32)
+                    self.pin_q[i].array[...] = fr.quality
+        self.out_ids = capi.PinnedBuffer((cap, 3), np.int32)
+        self.out_new = capi.PinnedBuffer((cap,), np.uint8)
+        self.out_upd = capi.PinnedBuffer((cap,), np.uint8)
+        self.out_q = capi.PinnedBuffer((cap,), np.float32)
+
+    def _ok(self, rc):
+        if rc != 0:
+            raise capi.TexFusionError(rc, self.L.tf_last_error(self.m.h).decode())
+
+    def upload(self, i):
+        fr = self.frames[i]
+        vp = C.c_void_p
+        self._ok(self.L.tf_upload_frame(self.m.h, fr.index, vp(self.pin_d[i].ptr),
+                                        vp(self.pin_c[i].ptr) if fr.is_keyframe else None,
+                                        vp(self.pin_q[i].ptr) if fr.is_keyframe else None))
+
+    def stage(self, i):
+        """Frame i on its way into every rank's frame store (asynchronous)."""
+        fr = self.frames[i]
+        if self.rank == 0:
+            self.upload(i)
+        if self.world > 1:
+            self._ok(self.L.tf_broadcast_frame(self.m.h, fr.index, int(fr.is_keyframe), 0))
+
+    def fuse(self, i):
+        fr = self.frames[i]
+        vp = C.c_void_p
+        if self.want_lists:
+            rc = self.L.tf_integrate_frame(self.m.h, fr.index, int(fr.is_keyframe), C.byref(self.poses[i]), C.byref(self.camc),
+                                           C.byref(self.st), vp(self.out_ids.ptr), vp(self.out_new.ptr), vp(self.out_upd.ptr),
+                                           vp(self.out_q.ptr), self.cap)
+        else:
+            rc = self.L.tf_integrate_frame(self.m.h, fr.index, int(fr.is_keyframe), C.byref(self.poses[i]), C.byref(self.camc),
+                                           C.byref(self.st), None, None, None, None, 0)
+        self._ok(rc)
+        return self.st.n_chunks
+
+    def wait(self, i):
+        self._ok(self.L.tf_wait_upload(self.m.h, self.frames[i].index))
+
+    def step(self, i):
+        """One end-to-end step for frame i (frame i must have been staged): next frame's ingest in
+        flight during this frame's kernels and finished inside the step."""
+        j = (i + 1) % self.nf
+        self.stage(j)
+        n = self.fuse(i)
+        self.wait(j)
+        return n
+
+    def lists(self):
+        """The last fused frame's ordered outputs (copies)."""
+        n = min(self.st.n_chunks, self.cap)
+        return (self.out_ids.array[:n].copy(), self.out_new.array[:n].copy(), self.out_upd.array[:n].copy(),
+                self.out_q.array[:n].copy())

@@ -1,9 +1,14 @@
-"""BASELINE.json configs[3] (C4), single GPU: a long walk through the 40 x 25 x 3 m building at 5 mm
-voxels.  Frames are rendered on the fly, uploaded from page-locked host memory and fused one call
-at a time (double buffered like bench.py's e2e leg); reports throughput per window of frames next
-to the size of the map, i.e. whether the per-frame cost depends on how much has been mapped.
+"""BASELINE.json configs[3] (C4): a long walk through the 40 x 25 x 3 m building at 5 mm voxels, on one GPU
+or chunk-sharded over N GPUs (one process per GPU, frames broadcast over NVLink by the library).
 
-  python tools/bench_building.py [--frames 2000] [--res 0.005] [--max-chunks 1048576]"""
+Frames are rendered on the fly on rank 0 (not timed), uploaded from page-locked host memory and fused one
+call at a time, double buffered like bench.py's e2e leg (upload + tf_broadcast_frame of frame k+1 in flight
+during the kernels of frame k).  Reports throughput per window of frames next to the size of the map —
+i.e. whether the per-frame cost depends on how much has been mapped — and at the end the chunks and HBM
+held per rank (load balance of the ownership hash) and the map checksum (texturefusion_b200.maphash).
+
+  python tools/bench_building.py [--frames 5000] [--res 0.005] [--max-chunks 4194304]
+  python -m torch.distributed.run --nproc-per-node N ... tools/bench_building.py --gpus N"""
 import argparse
 import ctypes as C
 import json
@@ -21,65 +26,125 @@ from texturefusion_b200 import capi, synth  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=2000)
+    ap.add_argument("--frames", type=int, default=5000)
     ap.add_argument("--total", type=int, default=5000, help="poses of the whole walk (frames are its first --frames)")
     ap.add_argument("--res", type=float, default=0.005)
-    ap.add_argument("--max-chunks", type=int, default=1 << 20)
-    ap.add_argument("--window", type=int, default=250)
+    ap.add_argument("--max-chunks", type=int, default=1 << 22, help="chunk pool of the whole job (split over the ranks, + 50 %% slack)")
+    ap.add_argument("--window", type=int, default=500)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--hash", action="store_true", help="also compute the checksum of the final map (downloads it)")
     args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(dev))
     cam = synth.Camera()
-    m = capi.Map(args.res, max_frames=8, max_chunks=args.max_chunks)
+    per_rank = args.max_chunks if world == 1 else int(args.max_chunks * 1.5 / world)
+    m = capi.Map(args.res, device=local_rank, n_ranks=world, rank=rank, max_frames=8, max_chunks=per_rank)
+    if dist is not None:
+        m.comm_init(capi.share_unique_id(dist, dev))
     L = m.L
     vp = C.c_void_p
     camc = capi.make_camera(cam)
     st = capi.FrameStats()
     npix = cam.width * cam.height
     pins = [(capi.PinnedBuffer((npix,), np.float32), capi.PinnedBuffer((npix * 4,), np.uint8), capi.PinnedBuffer((npix,), np.float32))
-            for _ in range(2)]
+            for _ in range(2)] if rank == 0 else None
 
-    def render(k):
+    def render(k):  # rank 0 only
         pose = synth.walk_pose(k, args.total)
         kf = k % 10 == 0
-        depth, rgb, q = synth.render(pose, cam, color=kf, device="cuda", scene="building")
+        depth, rgb, q = synth.render(pose, cam, color=kf, device=dev, scene="building")
         fr = synth.Frame(k, pose, depth, rgb, np.ones(depth.shape, np.uint8) if kf else None, q, kf)
         d, c, qq = pins[k & 1]
         d.array[:] = np.asarray(fr.depth, np.float32).ravel()
         if kf:
             c.array[:] = np.asarray(fr.rgba(), np.uint8).ravel()
             qq.array[:] = np.asarray(fr.quality, np.float32).ravel()
-        return fr
 
-    def upload(fr):
-        d, c, qq = pins[fr.index & 1]
-        rc = L.tf_upload_frame(m.h, fr.index, vp(d.ptr), vp(c.ptr) if fr.is_keyframe else None, vp(qq.ptr) if fr.is_keyframe else None)
-        assert rc == 0, L.tf_last_error(m.h)
+    def stage(k):
+        kf = k % 10 == 0
+        if rank == 0:
+            d, c, qq = pins[k & 1]
+            rc = L.tf_upload_frame(m.h, k, vp(d.ptr), vp(c.ptr) if kf else None, vp(qq.ptr) if kf else None)
+            assert rc == 0, L.tf_last_error(m.h)
+        if world > 1:
+            rc = L.tf_broadcast_frame(m.h, k, int(kf), 0)
+            assert rc == 0, L.tf_last_error(m.h)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     rows = []
-    cur = render(0)
-    upload(cur)
+    if rank == 0:
+        render(0)
+    stage(0)
     t_win, n_win, vox_win = 0.0, 0, 0
     for k in range(args.frames):
-        nxt = render(k + 1) if k + 1 < args.frames else None  # (rendering is not timed)
-        pose = capi.make_pose(cur.pose)
-        torch.cuda.synchronize()
+        has_next = k + 1 < args.frames
+        if has_next and rank == 0:
+            render(k + 1)  # (rendering is not timed)
+        pose = capi.make_pose(synth.walk_pose(k, args.total))
+        barrier()
         t0 = time.perf_counter()
-        if nxt is not None:
-            upload(nxt)
-        rc = L.tf_integrate_frame(m.h, cur.index, int(cur.is_keyframe), C.byref(pose), C.byref(camc), C.byref(st), None, None,
-                                  None, None, 0)
+        if has_next:
+            stage(k + 1)
+        rc = L.tf_integrate_frame(m.h, k, int(k % 10 == 0), C.byref(pose), C.byref(camc), C.byref(st), None, None, None, None, 0)
         assert rc == 0, L.tf_last_error(m.h)
-        if nxt is not None:
-            assert L.tf_wait_upload(m.h, nxt.index) == 0
+        if has_next:
+            assert L.tf_wait_upload(m.h, k + 1) == 0
         t_win += time.perf_counter() - t0
         n_win += 1
         vox_win += st.voxel_updates
-        if n_win == args.window or k + 1 == args.frames:
-            rows.append({"frames": k + 1, "fps_e2e": n_win / t_win, "chunks_per_frame": vox_win / 512 / n_win,
-                         "live_chunks": m.chunk_count(), "map_GB": m.chunk_count() * 8192 / 1e9})
-            print(json.dumps(rows[-1]), flush=True)
+        if n_win == args.window or not has_next:
+            stats = torch.tensor([t_win, float(vox_win), float(m.chunk_count())], dtype=torch.float64, device=dev)
+            if dist is not None:
+                tmax = stats.clone()
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                dist.all_reduce(stats)
+                t_job, vox_job, live = float(tmax[0]), float(stats[1]), float(stats[2])
+            else:
+                t_job, vox_job, live = t_win, float(vox_win), float(m.chunk_count())
+            if rank == 0:
+                rows.append({"frames": k + 1, "fps_e2e": n_win / t_job, "chunks_per_frame": vox_job / 512 / n_win,
+                             "voxel_updates_per_s": vox_job / t_job, "live_chunks": int(live), "map_GB": live * 8192 / 1e9})
+                print(json.dumps(rows[-1]), flush=True)
             t_win, n_win, vox_win = 0.0, 0, 0
-        cur = nxt
+    m.sync()
+    free_b, total_b = torch.cuda.mem_get_info()
+    mine = {"rank": rank, "chunks": int(m.chunk_count()), "map_GB": m.chunk_count() * 8192 / 1e9,
+            "hbm_used_GB": (total_b - free_b) / 1e9, "pool_capacity": per_rank}
+    if args.hash:
+        from texturefusion_b200.maphash import map_hash
+        mine["map_hash_part"] = map_hash(m)[1]
+    parts = [mine]
+    if dist is not None:
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(mine, parts, dst=0)
+    if rank == 0:
+        chunks = [p["chunks"] for p in parts]
+        total_frames = sum(1 for _ in range(args.frames))
+        total_t = sum((r["frames"] - (rows[i - 1]["frames"] if i else 0)) / r["fps_e2e"] for i, r in enumerate(rows))
+        line = {"metric": "building-scale fusion: frames/s end to end (upload + broadcast + fuse)", "n_gpus": world,
+                "value": total_frames / total_t, "unit": "frames/s",
+                "config": {"workload": f"configs[3]: {args.frames} frames of the {args.total}-pose walk through the 40x25x3 m building, "
+                                       f"{args.res} m voxels, chunk-sharded x{world}"},
+                "map_chunks": int(sum(chunks)), "active_voxels": int(sum(chunks)) * 512, "map_GB": sum(chunks) * 8192 / 1e9,
+                "per_rank": parts, "load_balance_max_over_mean": max(chunks) / (sum(chunks) / len(chunks)),
+                "windows": rows}
+        if args.hash:
+            line["map_hash"] = f"{sum(p['map_hash_part'] for p in parts) & ((1 << 64) - 1):016x}"
+        print(json.dumps(line), flush=True)
     m.close()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

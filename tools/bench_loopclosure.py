@@ -6,11 +6,14 @@ tf_integrate_batch call that de-integrates every key-frame group under its old p
 group's validChunks) and re-integrates it under the corrected poses — the loop of
 GCFusion/MobileFusion.cpp:301-310.  Frames stay resident in the map's frame store.
 
-  python tools/bench_loopclosure.py [--keyframes 50] [--res 0.005]
+  python tools/bench_loopclosure.py [--keyframes 500] [--res 0.005] [--verify]
   python -m torch.distributed.run --nproc-per-node N ... tools/bench_loopclosure.py --gpus N   (chunk-sharded)
 
 Prints one JSON line: key-frames/s, voxel updates/s, algorithmic GB/s of the integrate kernel and its
-fraction of the measured HBM peak (16 B per visited voxel, 32 B with colour)."""
+fraction of the measured HBM peak (16 B per visited voxel, 32 B with colour), plus
+`map_chunks` / `map_hash` (texturefusion_b200.maphash: shard-independent checksum of the final map, so
+the 1/2/4/8-GPU records can be compared with each other).  --verify replays the same item sequence on
+the CPU oracle (rank 0) and asserts that every chunk of the final map is bit-identical."""
 import argparse
 import json
 import os
@@ -27,13 +30,16 @@ from texturefusion_b200 import capi, synth  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--keyframes", type=int, default=50)
+    ap.add_argument("--keyframes", type=int, default=500)
     ap.add_argument("--group", type=int, default=7, help="frames per key-frame group (1 colour + local depth frames)")
     ap.add_argument("--res", type=float, default=0.005)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--repeat", type=int, default=3)
     ap.add_argument("--no-profile", action="store_true", help="no CUDA events around the integrate launches (no roofline figures)")
+    ap.add_argument("--verify", action="store_true", help="check the final map against the CPU oracle (forces --repeat 1)")
     args = ap.parse_args()
+    if args.verify:
+        args.repeat = 1
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -103,6 +109,44 @@ def main():
              "algorithmic_GBps_job": (k_bytes_all / 1e9) / dt}
         if best is None or r["seconds"] < best["seconds"]:
             best = r
+    from texturefusion_b200.maphash import sorted_chunk_hashes
+    m.sync()
+    ids, hs = sorted_chunk_hashes(m)
+    if dist is not None:
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object((ids, hs), parts, dst=0)
+        if rank == 0:
+            ids = np.concatenate([p[0] for p in parts])
+            hs = np.concatenate([p[1] for p in parts])
+            order = np.lexsort((ids[:, 2], ids[:, 1], ids[:, 0]))
+            ids, hs = ids[order], hs[order]
+    verified = None
+    if args.verify and rank == 0:
+        from oracle import OracleMap
+
+        def oracle_group(o, grp, old, flag, ids_=None):  # one ReIntegrateKeyframe call (GCFusion/MobileFusion.cpp:114-221)
+            kf = grp[0]
+            pose = (lambda fr: fr.pose_old) if old else (lambda fr: fr.pose)
+            if flag:
+                ids_, new = o.prepare(kf.depth, pose(kf), cam)
+                nu = np.zeros(len(ids_), np.uint8)
+            else:
+                new, nu = np.zeros(len(ids_), np.uint8), np.ones(len(ids_), np.uint8)
+            nu, _ = o.integrate(kf.depth, kf.rgba(), kf.quality, pose(kf), cam, ids_, flag, kf.index, nu)
+            for lf in grp[1:]:
+                nu, _ = o.integrate(lf.depth, None, None, pose(lf), cam, ids_, flag, -1, nu)
+            return o.finalize(ids_, nu, new)
+
+        t0 = time.perf_counter()
+        o = OracleMap(args.res, threads=0)
+        ov = [oracle_group(o, g, True, 1) for g in groups]
+        for k, g in enumerate(groups):
+            oracle_group(o, g, True, 0, ov[k])
+            oracle_group(o, g, False, 1)
+        oi, oh = sorted_chunk_hashes(o)
+        assert oi.shape == ids.shape and np.array_equal(oi, ids), f"chunk sets differ: {len(ids)} vs oracle {len(oi)}"
+        assert np.array_equal(oh, hs), f"{int((oh != hs).sum())} of {len(oi)} chunks differ from the CPU oracle"
+        verified = {"against": "CPU oracle (same item sequence)", "chunks": int(len(oi)), "oracle_seconds": time.perf_counter() - t0}
     if rank == 0:
         peak = 6549.8
         try:
@@ -119,7 +163,8 @@ def main():
                              "achieved": best["algorithmic_GBps_integrate"], "peak": peak, "unit": "GB/s",
                              "frac": best["algorithmic_GBps_integrate"] / peak, "launches": best["integrate_launches"],
                              "avg_launch_us": 1e3 * best["integrate_ms"] / max(best["integrate_launches"], 1)},
-                "job_algorithmic_GBps": best["algorithmic_GBps_job"], "seconds": best["seconds"]}
+                "job_algorithmic_GBps": best["algorithmic_GBps_job"], "seconds": best["seconds"],
+                "map_chunks": int(len(ids)), "map_hash": f"{int(hs.sum(dtype=np.uint64)):016x}", "verified": verified}
         print(json.dumps(line))
     m.close()
     if dist is not None:
