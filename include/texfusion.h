@@ -58,7 +58,8 @@ typedef struct { int32_t x, y, z; } tf_chunk_id;
 
 /* chisel::PinholeCamera (3rd_party/open_chisel/camera/PinholeCamera.h:33-75).  Pass the
  * float intrinsics given to SetIntrinsics; the library applies the int truncation of
- * GetFx/GetFy/GetCx/GetCy (:46-49) itself. */
+ * GetFx/GetFy/GetCx/GetCy (:46-49) itself.  width / height must be the frame size the map was
+ * created with and near_plane must be >= 0 (else TF_ERR_INVALID). */
 typedef struct {
   float fx, fy, cx, cy;
   int32_t width, height;

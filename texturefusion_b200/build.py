@@ -55,9 +55,20 @@ def build_timeline_variant() -> str:
     return out
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """An experimental build with extra -D flags (A/B runs: TEXFUSION_B200_LIB=<path> python bench.py ...);
+    written to build/variants/<name>.so (git-ignored, travels to the GPU box)."""
+    out = os.path.join(os.path.dirname(_PKG), "build", "variants", f"{name}.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.check_call([_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out, os.path.join(_CSRC, "tf_capi.cu")])
+    return out
+
+
 if __name__ == "__main__":
     import sys
     if len(sys.argv) > 1 and sys.argv[1] == "timeline":
         print(build_timeline_variant())
+    elif len(sys.argv) > 2 and sys.argv[1] == "variant":
+        print(build_variant(sys.argv[2], sys.argv[3:]))
     else:
         print(build_library(force=True, verbose=True))

@@ -253,7 +253,8 @@ inline void use_device(const tf_map* m) {
   if (cudaGetDevice(&cur) != cudaSuccess || cur != m->cfg.device) cudaSetDevice(m->cfg.device);
 }
 
-bool cam_ok(const tf_map* m, const tf_camera* c) { return c && c->width == m->W && c->height == m->H; }
+// (near_plane >= 0: integrate_kernel relies on masked-out gathers (depth 0) failing `depth > near`)
+bool cam_ok(const tf_map* m, const tf_camera* c) { return c && c->width == m->W && c->height == m->H && c->near_plane >= 0.0f; }
 
 // Slot of a stored frame, or -1.  for_compute: work is about to be queued on the compute stream
 // that reads the slot, so make that stream wait for the slot's uploads.
@@ -409,6 +410,20 @@ int launch_cull(tf_map* m, const CullParams& cp, const GroupParams& gp, const fl
   return check_kernel(m, "cull_kernel");
 }
 
+// The four instantiations of integrate_kernel: colour x single-frame.
+using IntegrateFn = void (*)(GroupParams, MapDev, const int*, const int*, const float*, const int*, int, unsigned*, float*,
+                             FusedFinalize);
+IntegrateFn integrate_fn(bool color, int n_frames) {
+  const bool single = n_frames == 1;
+  return color ? (single ? integrate_kernel<true, true> : integrate_kernel<true, false>)
+               : (single ? integrate_kernel<false, true> : integrate_kernel<false, false>);
+}
+void launch_integrate_kernel(tf_map* m, const GroupParams& gp, bool color, const int* n_dev, int n_host, const FusedFinalize& ff) {
+  launch_pdl(integrate_fn(color, gp.n_frames), color ? m->grid_integrate_c : m->grid_integrate,
+             integrate_smem_bytes(gp.n_frames, color), m->stream, gp, m->md, (const int*)m->cb.list_slots,
+             (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, n_dev, n_host, m->list_upd, m->list_q, ff);
+}
+
 int launch_integrate(tf_map* m, const GroupParams& gp, const int* n_dev, int n_host, double bytes,
                      const FusedFinalize* fused = nullptr) {
   FusedFinalize ff{};
@@ -417,14 +432,7 @@ int launch_integrate(tf_map* m, const GroupParams& gp, const int* n_dev, int n_h
   if (m->prof) prof_begin(m, ep);
   bool any_color = false;
   for (int f = 0; f < gp.n_frames; f++) any_color |= gp.f[f].rgba != nullptr;
-  if (any_color)
-    launch_pdl(integrate_kernel<true>, m->grid_integrate_c, integrate_smem_bytes(gp.n_frames, true), m->stream, gp, m->md,
-               (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, n_dev, n_host, m->list_upd,
-               m->list_q, ff);
-  else
-    launch_pdl(integrate_kernel<false>, m->grid_integrate, integrate_smem_bytes(gp.n_frames), m->stream, gp, m->md,
-               (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, n_dev, n_host, m->list_upd,
-               m->list_q, ff);
+  launch_integrate_kernel(m, gp, any_color, n_dev, n_host, ff);
   if (m->prof) {
     prof_end(m, ep);
     m->ev_pending.back().bytes = bytes;
@@ -608,13 +616,13 @@ int tf_create(tf_map** out, const tf_config* cfg) {
   C_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   C_OK(cudaEventCreateWithFlags(&m->reuse_ev, cudaEventDisableTiming));
   int occ = 1;
-  C_OK(cudaFuncSetAttribute(integrate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)integrate_smem_bytes(kMaxGroupFrames)));
-  C_OK(cudaFuncSetAttribute(integrate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)std::max(integrate_smem_bytes(kMaxGroupFrames, true), integrate_smem_bytes(1, true))));
+  for (int color = 0; color < 2; color++)
+    for (int nf : {1, kMaxGroupFrames})
+      C_OK(cudaFuncSetAttribute(integrate_fn(color, nf), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)integrate_smem_bytes(nf, color)));
   int occ_c = 1;
-  C_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, integrate_kernel<false>, kThreads, integrate_smem_bytes(1)));
-  C_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, integrate_kernel<true>, kThreads, integrate_smem_bytes(1, true)));
+  C_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, integrate_fn(false, 1), kThreads, integrate_smem_bytes(1)));
+  C_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, integrate_fn(true, 1), kThreads, integrate_smem_bytes(1, true)));
   m->grid_integrate_c = m->sm_count * std::max(1, occ_c);
   m->grid = m->sm_count * 2;
   m->grid_bbox = std::max(m->grid, (m->npix / 4 + kThreads - 1) / kThreads);  // one float4 per thread
@@ -1005,14 +1013,7 @@ static void launch_frame_kernels(tf_map* m, FrameArgs& a, bool profile = false) 
              m->cfg.rank, a.parity, a.want_order);
   EventPair ep;
   if (profile) prof_begin(m, ep);
-  if (a.any_color)
-    launch_pdl(integrate_kernel<true>, m->grid_integrate_c, integrate_smem_bytes(a.gp.n_frames, true), m->stream, a.gp, m->md,
-               (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, a.n_dev,
-               a.n_host, m->list_upd, m->list_q, a.ff);
-  else
-    launch_pdl(integrate_kernel<false>, m->grid_integrate, integrate_smem_bytes(a.gp.n_frames), m->stream, a.gp, m->md,
-               (const int*)m->cb.list_slots, (const int*)m->cb.list_hpos, (const float*)m->cb.list_setup, a.n_dev,
-               a.n_host, m->list_upd, m->list_q, a.ff);
+  launch_integrate_kernel(m, a.gp, a.any_color, a.n_dev, a.n_host, a.ff);
   if (profile) prof_end(m, ep);
   if (a.want_export) launch_pdl(export_kernel, export_grid(m), 0, m->stream, a.ex);
   m->counters.kernel_launches += a.want_export ? 4 : 3;
@@ -1046,7 +1047,7 @@ static bool build_frame_graph(tf_map* m, FrameGraph& fg, FrameArgs& a) {
   const size_t n_expected = a.want_export ? 4 : 3;
   if (cudaGraphGetNodes(g, nodes, &nn) != cudaSuccess || nn != n_expected) { cudaGetLastError(); return false; }
   const void* fn[4] = {(const void*)bbox_kernel, (const void*)cull_kernel<true>,
-                       a.any_color ? (const void*)integrate_kernel<true> : (const void*)integrate_kernel<false>,
+                       (const void*)integrate_fn(a.any_color, a.gp.n_frames),
                        (const void*)export_kernel};
   for (size_t i = 0; i < nn; i++) {
     cudaKernelNodeParams kp{};
