@@ -51,11 +51,19 @@ def main():
     dev = f"cuda:{local_rank}"
     cam = synth.Camera()
     n = args.keyframes * args.group
-    seq = synth.make_sequence(n, cam=cam, total=max(n, 300), keyframe_every=args.group, device=dev, with_drift=True)
-    groups = [seq.frames[k:k + args.group] for k in range(0, n, args.group)]
     m = capi.Map(args.res, device=local_rank, n_ranks=world, rank=rank, max_frames=n + 4, max_chunks=1 << 19)
-    for fr in seq.frames:
+    # every rank renders the (deterministic) sequence itself and keeps it resident in its frame store;
+    # the host copies of the images are dropped right away unless --verify needs them for the oracle
+    frames = []
+    total = max(n, 300)
+    for k in range(n):
+        fr = synth.make_sequence(1, cam=cam, total=total, keyframe_every=args.group, device=dev, with_drift=True, start=k).frames[0]
         m.upload_frame(fr.index, fr.depth, fr.rgba() if fr.is_keyframe else None, fr.quality if fr.is_keyframe else None)
+        if not (args.verify and rank == 0):
+            m.sync()
+            fr.depth = fr.rgb = fr.quality = fr.color_valid = None
+        frames.append(fr)
+    groups = [frames[k:k + args.group] for k in range(0, n, args.group)]
     m.sync()
 
     def item(group, flag, old, ids=None):
