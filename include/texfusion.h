@@ -240,6 +240,21 @@ int tf_list_chunks(tf_map* m, tf_chunk_id* out, int64_t cap, int64_t* n_out);
 int tf_download_chunks(tf_map* m, const tf_chunk_id* ids, int64_t n, float* sdf,
                        float* weight, uint16_t* color);
 
+/* ---- meshing ------------------------------------------------------------
+ * ChunkManager::RecomputeMeshes -> GenerateMeshEfficient (Structure/ChunkManager.cpp:232-264, 595-1002;
+ * gradient normals :277-455; triangle table 3rd_party/open_chisel/marching_cubes/MarchingCubes.cpp) for a
+ * list of chunks, on the voxels where they lie in HBM — replaces tf_download_chunks + the CPU mesher
+ * in the per-key-frame loop (Chisel::UpdateMeshes, GCFusion/MobileFusion.cpp:327).
+ * Chunk i owns vertices [vert_off[i], vert_off[i+1]) and indices [idx_off[i], idx_off[i+1])
+ * (vert_off / idx_off have n + 1 entries); vertices / normals / colors are xyz float triples in the
+ * order of mesh->vertices / normals / colors, indices are local to the chunk's vertex block like
+ * mesh->indices.  Ids that are not in the map give empty meshes (:239-241).  With all four output
+ * arrays NULL only the offsets are computed (size query); TF_ERR_CAPACITY if vert_cap (vertices)
+ * or idx_cap (indices) is too small — the offsets then hold the required sizes. */
+int tf_mesh_chunks(tf_map* m, const tf_chunk_id* ids, int64_t n, int64_t* vert_off, int64_t* idx_off,
+                   float* vertices, float* normals, float* colors, int32_t* indices, int64_t vert_cap,
+                   int64_t idx_cap);
+
 /* ---- texture atlas (Structure/Atlas.{h,cpp}) ---------------------------------------- */
 /* Atlas::AddPatch placement (Structure/Atlas.cpp:43-64): first call for an id hands out
  * loc_next and advances it; later calls return the same texloc. */

@@ -22,7 +22,7 @@ EXPORTS = [
     "tf_upload_frame", "tf_upload_keyframe_rgb", "tf_release_frame", "tf_frame_device_ptrs",
     "tf_comm_unique_id", "tf_comm_init", "tf_broadcast_frame",
     "tf_prepare", "tf_integrate", "tf_integrate_group", "tf_remove_chunks", "tf_integrate_frame",
-    "tf_integrate_batch", "tf_has_chunk", "tf_chunk_count", "tf_list_chunks", "tf_download_chunks",
+    "tf_integrate_batch", "tf_mesh_chunks", "tf_has_chunk", "tf_chunk_count", "tf_list_chunks", "tf_download_chunks",
     "tf_atlas_alloc_slot", "tf_atlas_update", "tf_atlas_download", "tf_atlas_patch_size", "tf_patch_texcoords", "tf_sync", "tf_wait_upload",
     "tf_get_counters", "tf_stream", "tf_copy_stream", "tf_set_profiling", "tf_get_kernel_time", "tf_get_stage_times", "tf_debug_project",
 ]
@@ -125,6 +125,7 @@ def load() -> C.CDLL:
     L.tf_chunk_count.restype = i64
     L.tf_list_chunks.argtypes = [vp, vp, i64, C.POINTER(i64)]
     L.tf_download_chunks.argtypes = [vp, vp, i64, vp, vp, vp]
+    L.tf_mesh_chunks.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, i64]
     L.tf_atlas_alloc_slot.argtypes = [vp, ChunkId, C.POINTER(C.c_uint64)]
     L.tf_atlas_update.argtypes = [vp, C.POINTER(PatchDesc), i64]
     L.tf_atlas_download.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
@@ -409,6 +410,22 @@ class Map:
         col = np.empty((n, 2048), np.uint16)
         self._check(self.L.tf_download_chunks(self.h, _p(ids), n, _p(sdf), _p(w), _p(col)))
         return sdf, w, col
+
+    def mesh_chunks(self, ids):
+        """ChunkManager::GenerateMeshEfficient per chunk on the device: (vert_off, idx_off, vertices,
+        normals, colors, indices)."""
+        ids = np.ascontiguousarray(ids, np.int32).reshape(-1, 3)
+        n = len(ids)
+        voff = np.zeros(n + 1, np.int64)
+        ioff = np.zeros(n + 1, np.int64)
+        self._check(self.L.tf_mesh_chunks(self.h, _p(ids), n, _p(voff), _p(ioff), None, None, None, None, 0, 0))
+        nv, ni = int(voff[-1]), int(ioff[-1])
+        vert = np.empty((max(nv, 1), 3), np.float32)
+        norm = np.empty((max(nv, 1), 3), np.float32)
+        col = np.empty((max(nv, 1), 3), np.float32)
+        idx = np.empty(max(ni, 1), np.int32)
+        self._check(self.L.tf_mesh_chunks(self.h, _p(ids), n, _p(voff), _p(ioff), _p(vert), _p(norm), _p(col), _p(idx), nv, ni))
+        return voff, ioff, vert[:nv], norm[:nv], col[:nv], idx[:ni]
 
     # atlas ---------------------------------------------------------------------------------
     def atlas_patch_size(self):

@@ -23,6 +23,7 @@
 #include "../../include/texfusion.h"
 #include "tf_host_math.h"
 #include "tf_kernels.cuh"
+#include "tf_mesh.cuh"
 
 using namespace tfb;
 
@@ -174,6 +175,12 @@ struct tf_map {
   PatchDev* patch_d = nullptr;
   int patch_cap = 0;
 
+  // grow-only device / page-locked arenas of the entry points that move variable-sized data
+  // (meshing, texcoords, chunk listing): no cudaMalloc / cudaFree in steady state
+  struct Arena { void* p = nullptr; size_t cap = 0; bool host = false; };
+  Arena ar_mesh_ids, ar_mesh_counts, ar_mesh_off, ar_mesh_v, ar_mesh_n, ar_mesh_c, ar_mesh_i, ar_mesh_off_h;
+  Arena ar_tc_off, ar_tc_v, ar_tc_c, ar_tc_tc, ar_tc_col, ar_tc_res, ar_list;
+
   // host mirrors
   int64_t n_live = 0;
   int pool_next = 0;
@@ -202,6 +209,22 @@ namespace {
       return TF_ERR_CUDA;                                                                      \
     }                                                                                          \
   } while (0)
+
+// grows (never shrinks) a device or page-locked host arena; the stream is drained before a buffer
+// that queued work may still use is released
+int ensure_arena_bytes(tf_map* m, tf_map::Arena& a, size_t need, bool host = false) {
+  if (need <= a.cap) return TF_OK;
+  cudaStreamSynchronize(m->stream);
+  if (a.p) { if (a.host) cudaFreeHost(a.p); else cudaFree(a.p); }
+  a.p = nullptr;
+  a.cap = 0;
+  const size_t cap = std::max<size_t>(need + need / 2, 4096);
+  const cudaError_t e = host ? cudaHostAlloc(&a.p, cap, cudaHostAllocDefault) : cudaMalloc(&a.p, cap);
+  if (e != cudaSuccess) { m->err = std::string("arena allocation: ") + cudaGetErrorString(e); return TF_ERR_CUDA; }
+  a.cap = cap;
+  a.host = host;
+  return TF_OK;
+}
 
 int fail(tf_map* m, int code, const std::string& msg) {
   if (m) m->err = msg;
@@ -533,6 +556,10 @@ void tf_destroy(tf_map* m) {
   cudaFreeHost(m->res_h); cudaFreeHost(m->out_ids_h); cudaFreeHost(m->out_new_h); cudaFreeHost(m->out_upd_h);
   cudaFreeHost(m->out_q_h); cudaFreeHost(m->upd_stage_h); cudaFreeHost(m->q_stage_h);
   cudaFree(m->slab);
+  for (tf_map::Arena* a : {&m->ar_mesh_ids, &m->ar_mesh_counts, &m->ar_mesh_off, &m->ar_mesh_v, &m->ar_mesh_n, &m->ar_mesh_c,
+                           &m->ar_mesh_i, &m->ar_mesh_off_h, &m->ar_tc_off, &m->ar_tc_v, &m->ar_tc_c, &m->ar_tc_tc,
+                           &m->ar_tc_col, &m->ar_tc_res, &m->ar_list})
+    if (a->p) { if (a->host) cudaFreeHost(a->p); else cudaFree(a->p); }
   cudaFree(m->st_ids); cudaFree(m->st_new); cudaFree(m->st_upd); cudaFree(m->st_q);
   cudaFreeHost(m->arena_ids); cudaFreeHost(m->arena_q); cudaFreeHost(m->arena_upd); cudaFreeHost(m->batch_rec);
   cudaFreeHost(m->ids_stage);
@@ -1491,6 +1518,61 @@ int tf_download_chunks(tf_map* m, const tf_chunk_id* ids, int64_t n, float* sdf,
     CUDA_OK(m, cudaStreamSynchronize(m->stream));
     m->counters.d2h_bytes += cnt * ((sdf ? 2048 : 0) + (weight ? 2048 : 0) + (color ? 4096 : 0));
   }
+  return TF_OK;
+}
+
+// ---- meshing -------------------------------------------------------------------------------------
+
+int tf_mesh_chunks(tf_map* m, const tf_chunk_id* ids, int64_t n, int64_t* vert_off, int64_t* idx_off, float* vertices,
+                   float* normals, float* colors, int32_t* indices, int64_t vert_cap, int64_t idx_cap) {
+  if (!m || n < 0 || (n > 0 && (!ids || !vert_off || !idx_off)) || n > (1 << 24))
+    return fail(m, TF_ERR_INVALID, "tf_mesh_chunks: bad argument");
+  const bool want = vertices || normals || colors || indices;
+  if (want && !(vertices && normals && colors && indices)) return fail(m, TF_ERR_INVALID, "tf_mesh_chunks: pass all four output arrays or none");
+  use_device(m);
+  if (vert_off) vert_off[0] = 0;
+  if (idx_off) idx_off[0] = 0;
+  if (n == 0) return TF_OK;
+  if (int rc = ensure_arena_bytes(m, m->ar_mesh_ids, (size_t)n * sizeof(int3))) return rc;
+  if (int rc = ensure_arena_bytes(m, m->ar_mesh_counts, (size_t)n * sizeof(int2))) return rc;
+  if (int rc = ensure_arena_bytes(m, m->ar_mesh_off, (size_t)(2 * n + 2) * sizeof(long long))) return rc;
+  if (int rc = ensure_arena_bytes(m, m->ar_mesh_off_h, (size_t)(2 * n + 2) * sizeof(long long), true)) return rc;
+  CUDA_OK(m, cudaMemcpyAsync(m->ar_mesh_ids.p, ids, (size_t)n * sizeof(int3), cudaMemcpyHostToDevice, m->stream));
+  m->counters.h2d_bytes += n * (int64_t)sizeof(int3);
+  MeshArgs a{};
+  a.ids = (const int3*)m->ar_mesh_ids.p;
+  a.n = (int)n;
+  a.res = m->cfg.voxel_res;
+  a.l2r = m->cfg.dot3_order;
+  a.counts = (int2*)m->ar_mesh_counts.p;
+  a.off = (const long long*)m->ar_mesh_off.p;
+  const int grid = (int)std::min<int64_t>(n, (int64_t)m->sm_count * 3);
+  mesh_kernel<false><<<grid, kMeshThreads, 0, m->stream>>>(m->md, a);
+  if (int rc = check_kernel(m, "mesh_kernel<count>")) return rc;
+  mesh_scan_kernel<<<1, 1024, 0, m->stream>>>(a.counts, a.n, (long long*)m->ar_mesh_off.p);
+  if (int rc = check_kernel(m, "mesh_scan_kernel")) return rc;
+  long long* off_h = (long long*)m->ar_mesh_off_h.p;
+  CUDA_OK(m, cudaMemcpyAsync(off_h, m->ar_mesh_off.p, (size_t)(2 * n + 2) * sizeof(long long), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  m->counters.d2h_bytes += (2 * n + 2) * (int64_t)sizeof(long long);
+  for (int64_t i = 0; i <= n; i++) { vert_off[i] = off_h[i]; idx_off[i] = off_h[n + 1 + i]; }
+  const int64_t nv = off_h[n], ni = off_h[2 * n + 1];
+  if (!want) return TF_OK;  // size query
+  if (nv > vert_cap || ni > idx_cap) return fail(m, TF_ERR_CAPACITY, "tf_mesh_chunks: output capacity too small (the offsets hold the required sizes)");
+  if (nv == 0) return TF_OK;
+  if (int rc = ensure_arena_bytes(m, m->ar_mesh_v, (size_t)nv * 12)) return rc;
+  if (int rc = ensure_arena_bytes(m, m->ar_mesh_n, (size_t)nv * 12)) return rc;
+  if (int rc = ensure_arena_bytes(m, m->ar_mesh_c, (size_t)nv * 12)) return rc;
+  if (int rc = ensure_arena_bytes(m, m->ar_mesh_i, (size_t)std::max<int64_t>(ni, 1) * 4)) return rc;
+  a.vert = (float*)m->ar_mesh_v.p, a.norm = (float*)m->ar_mesh_n.p, a.col = (float*)m->ar_mesh_c.p, a.idx = (int*)m->ar_mesh_i.p;
+  mesh_kernel<true><<<grid, kMeshThreads, 0, m->stream>>>(m->md, a);
+  if (int rc = check_kernel(m, "mesh_kernel<write>")) return rc;
+  CUDA_OK(m, cudaMemcpyAsync(vertices, a.vert, (size_t)nv * 12, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(m, cudaMemcpyAsync(normals, a.norm, (size_t)nv * 12, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(m, cudaMemcpyAsync(colors, a.col, (size_t)nv * 12, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(m, cudaMemcpyAsync(indices, a.idx, (size_t)ni * 4, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  m->counters.d2h_bytes += nv * 36 + ni * 4;
   return TF_OK;
 }
 
