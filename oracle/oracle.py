@@ -133,6 +133,8 @@ def _declare(L, full=False):
         L.tfo_get_observation.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int, f32p]
         L.tfo_meshes_to_update.restype = C.c_int64
         L.tfo_meshes_to_update.argtypes = [vp, vp, C.c_int64]
+        L.tfo_clear_meshes_to_update.argtypes = [vp]
+        L.tfo_retract_observations.argtypes = [vp, vp, C.c_int64, C.c_int]
         L.tfo_truncation_distance.restype = C.c_float
         L.tfo_truncation_distance.argtypes = [f32p, C.c_float]
         L.tfo_centroids.argtypes = [vp, vp, vp]
@@ -292,6 +294,13 @@ class OracleMap:
         out = np.empty((max(n, 1), 3), np.int32)
         self.L.tfo_meshes_to_update(self.h, _p(out), n)
         return out[:n]
+
+    def clear_meshes_to_update(self):
+        self.L.tfo_clear_meshes_to_update(self.h)
+
+    def retract_observations(self, ids, keyframe):
+        ids = np.ascontiguousarray(ids, np.int32).reshape(-1, 3)
+        self.L.tfo_retract_observations(self.h, _p(ids), len(ids), int(keyframe))
 
     def centroids(self, pose) -> np.ndarray:
         out = np.empty((3, 512), np.float32)

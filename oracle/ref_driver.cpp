@@ -347,6 +347,18 @@ int64_t tfo_meshes_to_update(tfo_map* h, int32_t* out, int64_t cap) {
   return i;
 }
 
+// Chisel::CompressMeshes ends with chunksToUpdate.clear() on meshesToUpdate (Structure/Chisel.cpp:146)
+void tfo_clear_meshes_to_update(tfo_map* h) { ((RefMap*)h)->meshesToUpdate.clear(); }
+// MobileFusion::RetractObservations (GCFusion/MobileFusion.cpp:252-272), the chunk half
+void tfo_retract_observations(tfo_map* h, const int32_t* ids, int64_t n, int keyframe) {
+  RefMap* m = (RefMap*)h;
+  for (int64_t i = 0; i < n; i++) {
+    const ChunkID id(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]);
+    if (!m->chunkManager.HasChunk(id)) continue;
+    m->chunkManager.GetChunk(id)->observations.erase(keyframe);
+  }
+}
+
 float tfo_truncation_distance(const float* t5, float z) { return QuadraticTruncator(t5[0], t5[1], t5[2], t5[3]).GetTruncationDistance(z); }
 
 void tfo_centroids(tfo_map* h, const float* pose, float* out3x512) {

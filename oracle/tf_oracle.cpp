@@ -626,6 +626,18 @@ int tfo_get_observation(tfo_map* h, int32_t x, int32_t y, int32_t z, int keyfram
   return 1;
 }
 
+// Chisel::CompressMeshes ends with chunksToUpdate.clear() on meshesToUpdate (Structure/Chisel.cpp:146)
+void tfo_clear_meshes_to_update(tfo_map* h) { ((Map*)h)->meshes_to_update.clear(); }
+// MobileFusion::RetractObservations (GCFusion/MobileFusion.cpp:252-272): chunk->observations.erase(frame_id)
+// for the listed chunks that are in the map
+void tfo_retract_observations(tfo_map* h, const int32_t* ids, int64_t n, int keyframe) {
+  Map& m = *(Map*)h;
+  for (int64_t i = 0; i < n; i++) {
+    auto it = m.chunks.find(Id3{ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]});
+    if (it != m.chunks.end()) it->second->observations.erase(keyframe);
+  }
+}
+
 int64_t tfo_meshes_to_update(tfo_map* h, int32_t* out, int64_t cap) {
   Map& m = *(Map*)h;
   int64_t i = 0;

@@ -1481,19 +1481,15 @@ int tf_list_chunks(tf_map* m, tf_chunk_id* out, int64_t cap, int64_t* n_out) {
   *n_out = m->n_live;
   if (m->n_live == 0) return TF_OK;
   if (cap < m->n_live || !out) return fail(m, TF_ERR_CAPACITY, "tf_list_chunks: output capacity too small");
-  int3* tmp = nullptr;
-  CUDA_OK(m, dmalloc(&tmp, (size_t)m->n_live));
+  if (int rc = ensure_arena_bytes(m, m->ar_list, (size_t)m->n_live * sizeof(int3))) return rc;
+  int3* tmp = (int3*)m->ar_list.p;
   cudaMemsetAsync(m->count_d, 0, sizeof(int), m->stream);
   list_kernel<<<m->grid, kThreads, 0, m->stream>>>(m->md, m->pool_next, tmp, (int)m->n_live, m->count_d);
-  int rc = check_kernel(m, "list_kernel");
-  if (!rc) {
-    cudaError_t e = cudaMemcpyAsync(out, tmp, (size_t)m->n_live * sizeof(int3), cudaMemcpyDeviceToHost, m->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
-    if (e != cudaSuccess) rc = fail(m, TF_ERR_CUDA, cudaGetErrorString(e));
-  }
-  cudaFree(tmp);
+  if (int rc = check_kernel(m, "list_kernel")) return rc;
+  CUDA_OK(m, cudaMemcpyAsync(out, tmp, (size_t)m->n_live * sizeof(int3), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
   m->counters.d2h_bytes += m->n_live * 12;
-  return rc;
+  return TF_OK;
 }
 
 int tf_download_chunks(tf_map* m, const tf_chunk_id* ids, int64_t n, float* sdf, float* weight, uint16_t* color) {
@@ -1674,36 +1670,33 @@ int tf_patch_texcoords(tf_map* m, int32_t frame_index, const tf_pose* world_to_c
   if (s < 0 || !m->slots[s].has_rgb) return fail(m, TF_ERR_NOT_FOUND, "tf_patch_texcoords: key-frame rgb not in the frame store");
   const int64_t nv = vertex_offsets[n_patches];
   if (nv < 0 || vertex_offsets[0] != 0) return fail(m, TF_ERR_INVALID, "tf_patch_texcoords: bad offsets");
-  long long* d_off = nullptr;
-  float *d_v = nullptr, *d_c = nullptr, *d_tc = nullptr, *d_col = nullptr;
-  PatchTexResult* d_res = nullptr;
-  int rc = TF_OK;
-  auto ok = [&](cudaError_t e) {
-    if (e != cudaSuccess && rc == TF_OK) rc = fail(m, TF_ERR_CUDA, cudaGetErrorString(e));
-    return e == cudaSuccess;
-  };
+  // grow-only arenas: no cudaMalloc / cudaFree per call
   const size_t nvv = (size_t)std::max<int64_t>(nv, 1);
-  if (ok(dmalloc(&d_off, (size_t)n_patches + 1)) && ok(dmalloc(&d_v, nvv * 3)) && ok(dmalloc(&d_c, nvv * 3)) &&
-      ok(dmalloc(&d_tc, nvv * 2)) && ok(dmalloc(&d_col, nvv * 3)) && ok(dmalloc(&d_res, (size_t)n_patches)) &&
-      ok(cudaMemcpyAsync(d_off, vertex_offsets, (n_patches + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, m->stream)) &&
-      ok(cudaMemcpyAsync(d_v, vertices, nv * 12, cudaMemcpyHostToDevice, m->stream)) &&
-      ok(cudaMemcpyAsync(d_c, colors, nv * 12, cudaMemcpyHostToDevice, m->stream))) {
-    tf_pose_dev T;
-    memcpy(T.m, world_to_camera->m, sizeof(T.m));
-    patch_texcoords_kernel<<<(unsigned)n_patches, kPatchThreads, 0, m->stream>>>(
-        m->slots[s].rgb, m->slots[s].depth, T, (float)(int)cam->fx, (float)(int)cam->fy, (float)(int)cam->cx,
-        (float)(int)cam->cy, m->W, m->H, d_off, d_v, d_c, d_tc, d_col, d_res);
-    ok(cudaGetLastError());
-    m->counters.kernel_launches++;
-    ok(cudaMemcpyAsync(texcoord_out, d_tc, nv * 8, cudaMemcpyDeviceToHost, m->stream));
-    ok(cudaMemcpyAsync(texcolor_out, d_col, nv * 12, cudaMemcpyDeviceToHost, m->stream));
-    ok(cudaMemcpyAsync(results, d_res, n_patches * sizeof(PatchTexResult), cudaMemcpyDeviceToHost, m->stream));
-    ok(cudaStreamSynchronize(m->stream));
-    m->counters.h2d_bytes += nv * 24 + (n_patches + 1) * 8;
-    m->counters.d2h_bytes += nv * 20 + n_patches * (int64_t)sizeof(PatchTexResult);
-  }
-  cudaFree(d_off); cudaFree(d_v); cudaFree(d_c); cudaFree(d_tc); cudaFree(d_col); cudaFree(d_res);
-  return rc;
+  if (int rc = ensure_arena_bytes(m, m->ar_tc_off, ((size_t)n_patches + 1) * 8)) return rc;
+  if (int rc = ensure_arena_bytes(m, m->ar_tc_v, nvv * 12)) return rc;
+  if (int rc = ensure_arena_bytes(m, m->ar_tc_c, nvv * 12)) return rc;
+  if (int rc = ensure_arena_bytes(m, m->ar_tc_tc, nvv * 8)) return rc;
+  if (int rc = ensure_arena_bytes(m, m->ar_tc_col, nvv * 12)) return rc;
+  if (int rc = ensure_arena_bytes(m, m->ar_tc_res, (size_t)n_patches * sizeof(PatchTexResult))) return rc;
+  long long* d_off = (long long*)m->ar_tc_off.p;
+  float *d_v = (float*)m->ar_tc_v.p, *d_c = (float*)m->ar_tc_c.p, *d_tc = (float*)m->ar_tc_tc.p, *d_col = (float*)m->ar_tc_col.p;
+  PatchTexResult* d_res = (PatchTexResult*)m->ar_tc_res.p;
+  CUDA_OK(m, cudaMemcpyAsync(d_off, vertex_offsets, (n_patches + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, m->stream));
+  CUDA_OK(m, cudaMemcpyAsync(d_v, vertices, nv * 12, cudaMemcpyHostToDevice, m->stream));
+  CUDA_OK(m, cudaMemcpyAsync(d_c, colors, nv * 12, cudaMemcpyHostToDevice, m->stream));
+  tf_pose_dev T;
+  memcpy(T.m, world_to_camera->m, sizeof(T.m));
+  patch_texcoords_kernel<<<(unsigned)n_patches, kPatchThreads, 0, m->stream>>>(
+      m->slots[s].rgb, m->slots[s].depth, T, (float)(int)cam->fx, (float)(int)cam->fy, (float)(int)cam->cx, (float)(int)cam->cy,
+      m->W, m->H, d_off, d_v, d_c, d_tc, d_col, d_res);
+  if (int rc = check_kernel(m, "patch_texcoords_kernel")) return rc;
+  CUDA_OK(m, cudaMemcpyAsync(texcoord_out, d_tc, nv * 8, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(m, cudaMemcpyAsync(texcolor_out, d_col, nv * 12, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(m, cudaMemcpyAsync(results, d_res, n_patches * sizeof(PatchTexResult), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  m->counters.h2d_bytes += nv * 24 + (n_patches + 1) * 8;
+  m->counters.d2h_bytes += nv * 20 + n_patches * (int64_t)sizeof(PatchTexResult);
+  return TF_OK;
 }
 
 // ---- counters / profiling ------------------------------------------------------------------------
