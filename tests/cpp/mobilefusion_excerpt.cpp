@@ -332,13 +332,17 @@ int main(int argc, char** argv) {
     std::vector<MultiViewGeometry::KeyFrameDatabase> kflist;
     std::vector<int> kf_indices;
     std::vector<float> tmp(npix);
+    std::vector<Sophus::SE3d> corrected(nfr), drifted(nfr);
     for (int k = 0; k < nfr; k++) {
       Frame& fr = frames[k];
       float pose[2][16];
       if (fread(pose, 4, 32, f) != 32) return 2;  // corrected pose, drifted pose (column-major)
-      for (int p = 0; p < 2; p++)
-        for (int c = 0; c < 4; c++)
-          for (int r = 0; r < 4; r++) fr.pose_sophus[p].M(r, c) = pose[p][c * 4 + r];
+      for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++) {
+          corrected[k].M(r, c) = pose[0][c * 4 + r];
+          drifted[k].M(r, c) = pose[1][c * 4 + r];
+        }
+      fr.pose_sophus[0] = fr.pose_sophus[1] = drifted[k];  // what tracking knows before the loop closure
       fr.frame_index = k;
       fr.is_keyframe = (k % group) == 0;
       if (fread(tmp.data(), 4, npix, f) != npix) return 2;
@@ -361,19 +365,14 @@ int main(int argc, char** argv) {
 
     if (bench > 0) {  // one key-frame group through the shim vs the same calls on the raw C ABI
       using clk = std::chrono::steady_clock;
-      // the first fusion is done under the drifted poses
-      for (auto& fr : frames) std::swap(fr.pose_sophus[0], fr.pose_sophus[1]);
-      mf.ReIntegrateKeyframe(frames, kflist[0], 1);
+      mf.ReIntegrateKeyframe(frames, kflist[0], 1);  // the first fusion, under the drifted poses
       double t_shim = 0, t_raw = 0;
       tf_map* m = mf.chiselMap->handle();
       const tf_camera cam = mf.cameraModel.c_camera();
       std::vector<unsigned char> rgba(npix * 4);
       Frame& kf = frames[kflist[0].keyFrameIndex];
-      for (size_t p = 0; p < npix; p++) {
-        const bool ok = kf.colorValidFlag.data[p] > 0;
-        for (int c = 0; c < 3; c++) rgba[p * 4 + c] = ok ? kf.rgb.data[p * 3 + c] : 0;
-        rgba[p * 4 + 3] = ok ? 1 : 0;
-      }
+      chisel::ChunkSet raw_meshes;  // the raw arm keeps the caller-side state of the protocol too
+      ChunkIDList raw_valid;
       std::vector<tf_chunk_id> ids(1 << 18);
       std::vector<uint8_t> isnew(1 << 18), nu(1 << 18);
       std::vector<float> q(1 << 18);
@@ -388,6 +387,11 @@ int main(int argc, char** argv) {
         for (int64_t i = 0; i < nv; i++) { ids[i] = chisel::to_c(kf.validChunks[i]); nu[i] = 1; }
         auto t2 = clk::now();
         auto run = [&](int flag, int64_t n) {
+          for (size_t p = 0; p < npix; p++) {  // the RGBA pack of ReIntegrateKeyframe (:151-162) is caller work in both arms
+            const bool ok = kf.colorValidFlag.data[p] > 0;
+            for (int c = 0; c < 3; c++) rgba[p * 4 + c] = ok ? kf.rgb.data[p * 3 + c] : 0;
+            rgba[p * 4 + 3] = ok ? 1 : 0;
+          }
           chisel::Transform T;
           T = kf.pose_sophus[flag ? 0 : 1].matrix().cast<float>();
           tf_pose pose = chisel::to_c(T);
@@ -403,10 +407,20 @@ int main(int argc, char** argv) {
             tf_upload_frame(m, 0x7F000000, (float*)frames[lf].refined_depth.data, nullptr, nullptr);
             tf_integrate(m, 0x7F000000, 0, &pose, &cam, ids.data(), n, flag, nu.data(), nullptr);
           }
-          std::vector<tf_chunk_id> garbage;
-          for (int64_t i = 0; i < n; i++)
-            if (flag && isnew[i] && !nu[i]) garbage.push_back(ids[i]);
+          std::vector<tf_chunk_id> garbage;  // FinalizeIntegrateChunks (Structure/Chisel.h:184-216)
+          raw_valid.clear();
+          for (int64_t i = 0; i < n; i++) {
+            if (nu[i]) {
+              const ChunkID id = chisel::from_c(ids[i]);
+              raw_meshes[id] = true;
+              for (int k = 0; k < 6; k++) raw_meshes[id + chisel::neighbourhood[k]] = true;
+              raw_valid.push_back(id);
+            } else if (flag && isnew[i]) {
+              garbage.push_back(ids[i]);
+            }
+          }
           if (!garbage.empty()) tf_remove_chunks(m, garbage.data(), (int64_t)garbage.size());
+          for (const tf_chunk_id& g : garbage) raw_meshes.erase(chisel::from_c(g));
           return n;
         };
         run(0, nv);
@@ -421,13 +435,13 @@ int main(int argc, char** argv) {
 
     FILE* out = fopen(argv[3], "wb");
     if (!out) return 2;
-    // 1. first fusion under the drifted poses (pose_sophus[1] holds the drifted pose on input)
-    for (auto& fr : frames) std::swap(fr.pose_sophus[0], fr.pose_sophus[1]);
+    // 1. first fusion under the drifted poses
     for (const auto& kfdb : kflist) mf.ReIntegrateKeyframe(frames, kfdb, 1);
     if (mf.MeshAndTexture(frames) < 0) return 3;
     dump_state(out, mf, frames, kf_indices);
-    // 2. loop closure of every key-frame: the corrected pose arrives in pose_sophus[0]
-    for (auto& fr : frames) std::swap(fr.pose_sophus[0], fr.pose_sophus[1]);  // [0] corrected, [1] what the map holds
+    // 2. loop closure of every key-frame: the corrected poses arrive in pose_sophus[0]; pose_sophus[1] is
+    //    what the map holds (set by ReIntegrateKeyframe(…, 1), GCFusion/MobileFusion.cpp:133-134)
+    for (int k = 0; k < nfr; k++) frames[k].pose_sophus[0] = corrected[k];
     for (const auto& kfdb : kflist) {
       mf.RetractObservations(mf.chiselMap->chunkManager, frames[kfdb.keyFrameIndex]);
       mf.ReIntegrateKeyframe(frames, kfdb, 0);

@@ -258,6 +258,9 @@ def check_stage(st, flow, textured, corrected, stage):
         tc, tcol, res = patch_texcoords(frames[k].rgb, frames[k].depth, rigid_inverse(corrected[k]), cam, off, verts, cols)
         for n, cid in enumerate(cids):
             p = st["meshes"][cid]["patch"]
+            if off[n + 1] == off[n]:  # the chunk's mesh became empty: its patch cannot be complete (Patch.cpp:191-196)
+                assert p is None
+                continue
             assert p is not None, f"{stage}: patch of {cid} incomplete"
             n_complete += 1
             assert p["frameid"] == k and p["box"] == tuple(int(v) for v in res[n][:4]) and p["wrong"] == int(res[n][4]), f"{stage}: patch of {cid}"
@@ -269,10 +272,14 @@ def check_stage(st, flow, textured, corrected, stage):
                 flow.atlas.atlas_update(p["texloc"], frames[k].rgb, p["box"])
     assert n_complete > 0, f"{stage}: nothing was textured"
     # atlas: the hot rows of the host mirror == the oracle's atlas; hot range as Structure/Chisel.cpp:184-186
-    locs = [st["meshes"][c]["patch"]["texloc"] for c in textured]
+    locs = [st["meshes"][c]["patch"]["texloc"] for c in textured if st["meshes"][c]["patch"] is not None]
     pw, ph = flow.atlas.atlas_patch_size()
     W = 13824
-    assert st["hot"] == ((min(locs) // W) * W, (max(locs) // W + ph) * W), f"{stage}: hot range"
+    # (patches of chunks whose mesh became empty also count in the reference's range, but are not dumped)
+    assert st["hot"][0] % W == 0 and st["hot"][1] % W == 0 and st["hot"][0] <= (min(locs) // W) * W and \
+        st["hot"][1] >= (max(locs) // W + ph) * W, f"{stage}: hot range"
+    if all(st["meshes"][c]["patch"] is not None for c in textured):
+        assert st["hot"] == ((min(locs) // W) * W, (max(locs) // W + ph) * W), f"{stage}: hot range"
     want = flow.atlas.atlas_download(st["hot"][0], min(st["hot"][1], W * W))
     assert np.array_equal(st["hot_bytes"][:len(want)], want), f"{stage}: atlas hot rows differ from the oracle"
     # GL buffers: every complete patch contributes its mesh
@@ -335,7 +342,7 @@ def test_mobilefusion_flow_through_the_shim_matches_oracle(tmp_path, res, scale)
 def test_shim_per_keyframe_time_close_to_raw_c_abi(tmp_path):
     cam = synth.Camera()
     group = 7
-    seq = synth.make_sequence(group, cam=cam, total=300, keyframe_every=group, start=40, with_drift=True)
+    seq = synth.make_sequence(group, cam=cam, total=300, keyframe_every=group, start=42, with_drift=True)
     path = tmp_path / "in.bin"
     with open(path, "wb") as f:
         f.write(struct.pack("<4i", cam.width, cam.height, group, group))

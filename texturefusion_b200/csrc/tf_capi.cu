@@ -111,6 +111,7 @@ struct tf_map {
   cudaStream_t stream = nullptr;       // all kernels and read-backs
   cudaStream_t copy_stream = nullptr;  // frame uploads: the next frame's H2D copy overlaps the current frame's kernels
   cudaEvent_t reuse_ev = nullptr;      // orders an overwriting upload behind the kernels that read the slot
+  cudaEvent_t patch_copy_done = nullptr;  // tf_atlas_update: the descriptor copy has left the page-locked arena
   std::string err;
   unsigned char* slab = nullptr;        // frame store: per slot [depth | rgba | quality | rgb | valid], contiguous so
   size_t slot_stride = 0;               // that one broadcast moves depth (+ rgba + quality) of a frame
@@ -172,14 +173,12 @@ struct tf_map {
   uint64_t loc_next = 0;
   int patch_w = 0, patch_h = 0;
   std::unordered_map<unsigned long long, uint64_t> patches;
-  PatchDev* patch_d = nullptr;
-  int patch_cap = 0;
 
   // grow-only device / page-locked arenas of the entry points that move variable-sized data
   // (meshing, texcoords, chunk listing): no cudaMalloc / cudaFree in steady state
   struct Arena { void* p = nullptr; size_t cap = 0; bool host = false; };
   Arena ar_mesh_ids, ar_mesh_counts, ar_mesh_off, ar_mesh_v, ar_mesh_n, ar_mesh_c, ar_mesh_i, ar_mesh_off_h;
-  Arena ar_tc_off, ar_tc_v, ar_tc_c, ar_tc_tc, ar_tc_col, ar_tc_res, ar_list;
+  Arena ar_tc_off, ar_tc_v, ar_tc_c, ar_tc_tc, ar_tc_col, ar_tc_res, ar_list, ar_patch_h, ar_patch_d;
 
   // host mirrors
   int64_t n_live = 0;
@@ -546,19 +545,20 @@ void tf_destroy(tf_map* m) {
     if (sl.ready) cudaEventDestroy(sl.ready);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->reuse_ev) cudaEventDestroy(m->reuse_ev);
+  if (m->patch_copy_done) cudaEventDestroy(m->patch_copy_done);
   cudaFree(m->md.table); cudaFree(m->md.pool); cudaFree(m->md.slot_id);
   cudaFree(m->md.slot_flags); cudaFree(m->md.free_stack); cudaFree(m->fs);
   cudaFree(m->cb.mask32); cudaFree(m->cb.local_off); cudaFree(m->cb.hit_items); cudaFree(m->cb.hit_count);
   cudaFree(m->cb.word_base); cudaFree(m->cb.list_cb); cudaFree(m->cb.list_hpos);
   cudaFree(m->partial); cudaFree(m->cb.list_ids); cudaFree(m->cb.list_slots); cudaFree(m->cb.list_new);
   cudaFree(m->list_upd); cudaFree(m->list_q); cudaFree(m->cb.list_setup); cudaFree(m->dl_sdf); cudaFree(m->dl_w); cudaFree(m->dl_col);
-  cudaFree(m->count_d); cudaFree(m->atlas); cudaFree(m->patch_d);
+  cudaFree(m->count_d); cudaFree(m->atlas);
   cudaFreeHost(m->res_h); cudaFreeHost(m->out_ids_h); cudaFreeHost(m->out_new_h); cudaFreeHost(m->out_upd_h);
   cudaFreeHost(m->out_q_h); cudaFreeHost(m->upd_stage_h); cudaFreeHost(m->q_stage_h);
   cudaFree(m->slab);
   for (tf_map::Arena* a : {&m->ar_mesh_ids, &m->ar_mesh_counts, &m->ar_mesh_off, &m->ar_mesh_v, &m->ar_mesh_n, &m->ar_mesh_c,
                            &m->ar_mesh_i, &m->ar_mesh_off_h, &m->ar_tc_off, &m->ar_tc_v, &m->ar_tc_c, &m->ar_tc_tc,
-                           &m->ar_tc_col, &m->ar_tc_res, &m->ar_list})
+                           &m->ar_tc_col, &m->ar_tc_res, &m->ar_list, &m->ar_patch_h, &m->ar_patch_d})
     if (a->p) { if (a->host) cudaFreeHost(a->p); else cudaFree(a->p); }
   cudaFree(m->st_ids); cudaFree(m->st_new); cudaFree(m->st_upd); cudaFree(m->st_q);
   cudaFreeHost(m->arena_ids); cudaFreeHost(m->arena_q); cudaFreeHost(m->arena_upd); cudaFreeHost(m->batch_rec);
@@ -1619,7 +1619,13 @@ int tf_atlas_update(tf_map* m, const tf_patch_desc* patches, int64_t n) {
   use_device(m);
   if (n == 0) return TF_OK;
   if (int rc = ensure_atlas(m)) return rc;
-  std::vector<PatchDev> pd((size_t)n);
+  // descriptors are assembled in a page-locked arena (a pageable source would be staged by the runtime
+  // with an extra copy and a stall) and the device copy of the list is a grow-only arena as well
+  if (m->patch_w > kAtlasMaxPW || m->patch_h > kAtlasMaxPH) return fail(m, TF_ERR_INVALID, "tf_atlas_update: slot larger than 96 x 72 (voxels > 20 mm)");
+  if (int rc = ensure_arena_bytes(m, m->ar_patch_h, (size_t)n * sizeof(PatchDev), true)) return rc;
+  if (int rc = ensure_arena_bytes(m, m->ar_patch_d, (size_t)n * sizeof(PatchDev))) return rc;
+  if (m->patch_copy_done) cudaEventSynchronize(m->patch_copy_done);  // the previous call's H2D copy has left the host arena
+  PatchDev* pd = (PatchDev*)m->ar_patch_h.p;
   for (int64_t i = 0; i < n; i++) {
     const tf_patch_desc& p = patches[i];
     const int s = find_slot(m, p.frame_index);
@@ -1632,14 +1638,12 @@ int tf_atlas_update(tf_map* m, const tf_patch_desc* patches, int64_t n) {
     if (ox + ew > kAtlasDim || oy + eh > kAtlasDim) return fail(m, TF_ERR_INVALID, "tf_atlas_update: slot outside the atlas");
     pd[i] = PatchDev{p.texloc, m->slots[s].rgb, p.x, p.y, p.w, p.h};
   }
-  if (n > m->patch_cap) {
-    cudaFree(m->patch_d);
-    m->patch_cap = (int)std::max<int64_t>(n, 4096);
-    CUDA_OK(m, dmalloc(&m->patch_d, (size_t)m->patch_cap));
-  }
-  // pageable source: the copy is staged before the call returns, so `pd` may go out of scope
-  CUDA_OK(m, cudaMemcpyAsync(m->patch_d, pd.data(), (size_t)n * sizeof(PatchDev), cudaMemcpyHostToDevice, m->stream));
-  atlas_update_kernel<<<(unsigned)n, kThreads, 0, m->stream>>>(m->patch_d, m->atlas, m->W, m->patch_w, m->patch_h);
+  CUDA_OK(m, cudaMemcpyAsync(m->ar_patch_d.p, pd, (size_t)n * sizeof(PatchDev), cudaMemcpyHostToDevice, m->stream));
+  if (!m->patch_copy_done) CUDA_OK(m, cudaEventCreateWithFlags(&m->patch_copy_done, cudaEventDisableTiming));
+  CUDA_OK(m, cudaEventRecord(m->patch_copy_done, m->stream));
+  const int grid = (int)std::min<int64_t>((n + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)m->sm_count * 8);
+  atlas_update_kernel<<<grid, kThreads, 0, m->stream>>>((const PatchDev*)m->ar_patch_d.p, (int)n, m->atlas, m->W, m->H, m->patch_w,
+                                                        m->patch_h);
   if (int rc = check_kernel(m, "atlas_update_kernel")) return rc;
   m->counters.h2d_bytes += n * (int64_t)sizeof(PatchDev);
   return TF_OK;
