@@ -6,7 +6,7 @@
 // KeyFrameDatabase, Sophus::SE3d, cv::Mat, UniGraph) are stubbed with the members the calls touch.
 // Compiled with -DTF_WITH_EIGEN against the Eigen stand-in of oracle/eigen_standin (tests only).
 //
-//   mobilefusion_excerpt <input.bin> <voxel_res> <output.bin> [--bench N]
+//   mobilefusion_excerpt <input.bin> <voxel_res> <output.bin> [--bench N] [--export DIR]
 //
 // Runs: K key-frame groups through ReIntegrateKeyframe(…, 1); the tsdfFusion tail; a loop closure of
 // key-frame 0 (Retract + ReIntegrate 0 + ReIntegrate 1 under a corrected pose); the tail again; dumps
@@ -303,8 +303,11 @@ int main(int argc, char** argv) {
   if (!f) return 2;
   const float res = (float)atof(argv[2]);
   int bench = 0;
-  for (int i = 4; i + 1 < argc; i++)
+  std::string export_dir;
+  for (int i = 4; i + 1 < argc; i++) {
     if (std::string(argv[i]) == "--bench") bench = atoi(argv[i + 1]);
+    if (std::string(argv[i]) == "--export") export_dir = argv[i + 1];
+  }
   int32_t hdr[4];  // W, H, n_frames, group size
   if (fread(hdr, 4, 4, f) != 4) return 2;
   const int W = hdr[0], H = hdr[1], nfr = hdr[2], group = hdr[3];
@@ -449,6 +452,11 @@ int main(int argc, char** argv) {
     }
     if (mf.MeshAndTexture(frames) < 0) return 3;
     dump_state(out, mf, frames, kf_indices);
+    if (!export_dir.empty()) {  // main.cpp:263-270: PLY of the meshes, OBJ + MTL + image of the textured model
+      if (!mf.chiselMap->SaveAllMeshesToPLY(export_dir + "/model.ply")) return 4;
+      const std::size_t rows = mf.chiselMap->atlas.hot_end / chisel::Atlas::MAX_PATCH_WIDTH;
+      mf.chiselMap->atlas.SaveTexturedModel(export_dir, rows);
+    }
     // 3. a plain frame through the fused convenience form (IntegrateFrame)
     mf.IntegrateFrame(frames[1]);
     put_i64(out, mf.chiselMap->last_stats.n_chunks);

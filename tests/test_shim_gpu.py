@@ -287,6 +287,35 @@ def check_stage(st, flow, textured, corrected, stage):
     assert st["n_vert"] == sum(len(m["vert"]) for m in complete) and st["n_idx"] == sum(len(m["idx"]) for m in complete)
 
 
+def check_exports(folder, st):
+    """SaveAllMeshesToPLY / SaveTexturedModel (Structure/Chisel.cpp:357-379, io/PLY.cpp, Structure/Atlas.cpp:93-179):
+    file layouts as the reference writes them, contents consistent with the dumped state."""
+    n_idx_all = sum(len(m["idx"]) for m in st["meshes"].values())
+    ply = open(os.path.join(folder, "model.ply")).read().split("\n")
+    assert ply[0] == "ply" and ply[1] == "format ascii 1.0" and ply[2] == f"element vertex {n_idx_all}"
+    end = ply.index("end_header")
+    assert f"element face {n_idx_all // 3}" in ply[:end] and "property uchar red" in ply[:end]
+    body = [ln for ln in ply[end + 1:] if ln.strip()]
+    assert len(body) == n_idx_all + n_idx_all // 3
+    assert len(body[0].split()) == 6 and body[n_idx_all].split()[0] == "3"
+    complete = [m for m in st["meshes"].values() if m["patch"] is not None and len(m["patch"]["tc"]) == len(m["vert"])]
+    nv, nf = sum(len(m["vert"]) for m in complete), sum(len(m["idx"]) for m in complete) // 3
+    obj = open(os.path.join(folder, "texture_model.obj")).read().split("\n")
+    assert obj[0] == "mtllib texture_model.mtl"
+    assert sum(ln.startswith("v ") for ln in obj) == nv and sum(ln.startswith("vt ") for ln in obj) == nv
+    assert sum(ln.startswith("vn ") for ln in obj) == nv and sum(ln.startswith("f ") for ln in obj) == nf
+    vt = np.array([[float(x) for x in ln.split()[1:]] for ln in obj if ln.startswith("vt ")])
+    assert len(vt) == 0 or (vt.min() >= -1e-3 and vt.max() <= 1 + 1e-3)
+    mtl = open(os.path.join(folder, "texture_model.mtl")).read()
+    assert "newmtl demo_texture" in mtl and "map_Kd texture_material.ppm" in mtl
+    with open(os.path.join(folder, "texture_material.ppm"), "rb") as f:
+        assert f.readline() == b"P6\n"
+        w, h = (int(x) for x in f.readline().split())
+        assert f.readline() == b"255\n" and w == 13824 and h * w == st["hot"][1]
+        img = np.frombuffer(f.read(), np.uint8)
+    assert np.array_equal(img[3 * st["hot"][0]:], st["hot_bytes"]), "exported texture differs from the atlas hot rows"
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("res,scale", ((0.02, 1.0), (0.005, 0.25)))
 def test_mobilefusion_flow_through_the_shim_matches_oracle(tmp_path, res, scale):
@@ -311,7 +340,9 @@ def test_mobilefusion_flow_through_the_shim_matches_oracle(tmp_path, res, scale)
                 f.write(np.ascontiguousarray(fr.color_valid, np.uint8).tobytes())
                 f.write(np.ascontiguousarray(fr.quality, np.float32).tobytes())
     exe = build_excerpt(str(tmp_path))
-    out = subprocess.run([exe, str(path), repr(res), str(outp)], capture_output=True, text=True, timeout=600)
+    exp = tmp_path / "export"
+    exp.mkdir()
+    out = subprocess.run([exe, str(path), repr(res), str(outp), "--export", str(exp)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr + out.stdout
     r = Reader(str(outp))
     drift = [fr.pose_old for fr in frames]
@@ -331,6 +362,7 @@ def test_mobilefusion_flow_through_the_shim_matches_oracle(tmp_path, res, scale)
     st2 = read_state(r)
     textured = flow.mesh_and_texture()
     check_stage(st2, flow, textured, corrected, "stage 2")
+    check_exports(str(exp), st2)
     # stage 3: IntegrateFrame (fused convenience form) of a depth-only frame
     n, n_upd = flow.o.integrate_frame(frames[1].depth, None, None, corrected[1], cam, -1)
     assert (r.i64(), r.i64()) == (n, n_upd)

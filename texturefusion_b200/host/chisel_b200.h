@@ -24,6 +24,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iomanip>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -42,6 +45,8 @@
 #endif
 #ifdef TF_WITH_OPENCV
 #include <opencv2/core.hpp>
+#include <opencv2/imgcodecs.hpp>
+#include <opencv2/imgproc.hpp>
 #endif
 
 namespace chisel {
@@ -508,6 +513,71 @@ class Atlas {
     const int rc = tf_atlas_download(map, hot_start, end, host_pixels + hot_start * 3);
     if (rc < 0) throw TexFusionError(rc, tf_last_error(map));
   }
+  // Atlas::SaveTexturedModel (Structure/Atlas.cpp:93-179): texture_model.obj / .mtl + the atlas image.
+  // With OpenCV the image is texture_material.png like the reference; without, a binary PPM
+  // (texture_material.ppm, same pixels) — the .mtl names the file that was written.  `rows` limits the
+  // image to its first rows (0 = all 13824; every slot in use lies above loc_next's row + PATCH_HEIGHT).
+  void SaveTexturedModel(const std::string& basepath, std::size_t rows = 0) {
+    if (rows == 0 || rows > MAX_PATCH_HEIGHT) rows = MAX_PATCH_HEIGHT;
+    const std::size_t keep_start = hot_start, keep_end = hot_end;
+    hot_start = 0;
+    hot_end = rows * MAX_PATCH_WIDTH;
+    SyncHotRange();  // the whole image (or its first rows) from HBM into the host mirror
+    hot_start = keep_start;
+    hot_end = keep_end;
+#ifdef TF_WITH_OPENCV
+    const std::string tex_name = "texture_material.png";
+    cv::Mat texture_bgr;
+    cv::cvtColor(texture_buffer(cv::Rect(0, 0, (int)MAX_PATCH_WIDTH, (int)rows)), texture_bgr, cv::COLOR_RGB2BGR);
+    cv::imwrite(basepath + "/" + tex_name, texture_bgr);
+#else
+    const std::string tex_name = "texture_material.ppm";
+    {
+      std::ofstream img((basepath + "/" + tex_name).c_str(), std::ios::binary);
+      img << "P6\n" << MAX_PATCH_WIDTH << " " << rows << "\n255\n";
+      img.write((const char*)texture_buffer.data, (std::streamsize)(rows * MAX_PATCH_WIDTH * 3));
+    }
+#endif
+    Vec3List vertices, normals;
+    Vec2List texcoords;
+    VertIndexList indices;
+    std::size_t vts = 0;
+    for (auto& it : manager->GetAllMeshes()) {
+      MeshPtr mesh = it.second;
+      PatchPtr patch = mesh->m_patch;
+      if (patch == nullptr || !patch->complete() || patch->texcoord.size() != mesh->vertices.size()) continue;
+      for (std::size_t j = 0; j < mesh->indices.size(); j++) indices.emplace_back(mesh->indices[j] + vts);
+      const Vec2 loc = GetTexLoc(mesh->chunkID);
+      for (std::size_t j = 0; j < mesh->vertices.size(); j++) {
+        vertices.emplace_back(mesh->vertices[j]);
+        normals.emplace_back(mesh->normals[j]);
+        Vec2 tex = loc;
+        tex(0) += patch->texcoord[j](0) * patch->ratio(0);
+        tex(1) += patch->texcoord[j](1) * patch->ratio(1);
+        tex(0) /= MAX_PATCH_WIDTH;
+        tex(1) /= MAX_PATCH_HEIGHT;
+        texcoords.emplace_back(tex);
+        vts++;
+      }
+    }
+    std::ofstream mout((basepath + "/texture_model.obj").c_str());
+    mout << "mtllib texture_model.mtl" << '\n' << std::fixed << std::setprecision(6);
+    for (std::size_t i = 0; i < vertices.size(); ++i) mout << "v " << vertices[i](0) << " " << vertices[i](1) << " " << vertices[i](2) << '\n';
+    for (std::size_t i = 0; i < texcoords.size(); ++i) mout << "vt " << texcoords[i](0) << " " << 1.0f - texcoords[i](1) << '\n';
+    for (std::size_t i = 0; i < normals.size(); ++i) mout << "vn " << normals[i](0) << " " << normals[i](1) << " " << normals[i](2) << '\n';
+    mout << "s off" << '\n' << "usemtl demo_texture" << '\n';
+    for (std::size_t i = 0; i < indices.size() / 3; ++i) {
+      mout << "g face" << i << '\n' << "f";
+      for (std::size_t k = 0; k < 3; ++k) mout << " " << indices[i * 3 + k] + 1 << "/" << indices[i * 3 + k] + 1 << "/" << indices[i * 3 + k] + 1;
+      mout << '\n';
+    }
+    mout.close();
+    std::ofstream out((basepath + "/texture_model.mtl").c_str());
+    out << "newmtl demo_texture" << '\n' << "Ka 1.000000 1.000000 1.000000" << '\n' << "Kd 1.000000 1.000000 1.000000" << '\n'
+        << "Ks 0.000000 0.000000 0.000000" << '\n' << "Tr 0.000000" << '\n' << "illum 1" << '\n' << "Ns 1.000000" << '\n'
+        << "map_Kd " << tex_name << std::endl;
+  }
+
   void DownloadRows(std::size_t start, std::size_t end, uint8_t* rgb) {
     const int rc = tf_atlas_download(map, start, end, rgb);
     if (rc < 0) throw TexFusionError(rc, tf_last_error(map));
@@ -856,6 +926,29 @@ class Chisel {
     }
     tsdf_indice_num = index_num;
     tsdf_vertice_num = vert_num;
+  }
+
+  // Chisel::SaveAllMeshesToPLY (Structure/Chisel.cpp:357-379) + SaveMeshPLYASCII
+  // (3rd_party/open_chisel/io/PLY.cpp:27-80): one vertex per index, ASCII, colours as uchar
+  bool SaveAllMeshesToPLY(const std::string& filename) {
+    std::size_t v = 0;
+    for (const auto& it : chunkManager.GetAllMeshes()) v += it.second->indices.size();
+    std::ofstream stream(filename.c_str());
+    if (!stream) return false;
+    stream << "ply" << std::endl << "format ascii 1.0" << std::endl << "element vertex " << v << std::endl;
+    stream << "property float x" << std::endl << "property float y" << std::endl << "property float z" << std::endl;
+    if (v > 0) stream << "property uchar red" << std::endl << "property uchar green" << std::endl << "property uchar blue" << std::endl;
+    stream << "element face " << v / 3 << std::endl << "property list uchar int vertex_index" << std::endl << "end_header" << std::endl;
+    for (const auto& it : chunkManager.GetAllMeshes()) {
+      const Mesh& m = *it.second;
+      for (std::size_t i = 0; i < m.indices.size(); i++) {
+        const Vec3 &vert = m.vertices[m.indices[i]], &color = m.colors[m.indices[i]];
+        stream << vert(0) << " " << vert(1) << " " << vert(2) << " " << static_cast<int>(color(0) * 255.0f) << " "
+               << static_cast<int>(color(1) * 255.0f) << " " << static_cast<int>(color(2) * 255.0f) << std::endl;
+      }
+    }
+    for (std::size_t i = 0; i + 2 < v; i += 3) stream << "3 " << i << " " << i + 1 << " " << i + 2 << " " << std::endl;
+    return (bool)stream;
   }
 
   tf_map* handle() { return map; }
