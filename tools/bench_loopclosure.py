@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--repeat", type=int, default=3)
     ap.add_argument("--no-profile", action="store_true", help="no CUDA events around the integrate launches (no roofline figures)")
+    ap.add_argument("--fake-ranks", type=int, default=0, help="single process, but the map only owns rank 0's share of N ranks "
+                    "(what one GPU of an N-GPU job does, without the other N-1)")
     ap.add_argument("--verify", action="store_true", help="check the final map against the CPU oracle (forces --repeat 1)")
     args = ap.parse_args()
     if args.verify:
@@ -51,7 +53,7 @@ def main():
     dev = f"cuda:{local_rank}"
     cam = synth.Camera()
     n = args.keyframes * args.group
-    m = capi.Map(args.res, device=local_rank, n_ranks=world, rank=rank, max_frames=n + 4, max_chunks=1 << 19)
+    m = capi.Map(args.res, device=local_rank, n_ranks=args.fake_ranks or world, rank=rank, max_frames=n + 4, max_chunks=1 << 19)
     # every rank renders the (deterministic) sequence itself and keeps it resident in its frame store;
     # the host copies of the images are dropped right away unless --verify needs them for the oracle
     frames = []
