@@ -205,6 +205,16 @@ int tf_integrate_frame(tf_map* m, int32_t frame_index, int use_color, const tf_p
                        const tf_camera* cam, tf_frame_stats* stats_out, tf_chunk_id* ids_out,
                        uint8_t* is_new_out, uint8_t* updated_out, float* quality_out, int64_t cap);
 
+/* The same call in two halves, for a streaming caller: _begin queues the frame's kernels and returns at
+ * once; between _begin and _end only frame-store calls of OTHER frames are allowed (tf_upload_frame,
+ * tf_broadcast_frame, tf_wait_upload: the next frame's ingest then overlaps this frame's kernels on
+ * the host side too); _end waits, fills the output arrays handed to _begin and returns the frame's
+ * status.  tf_integrate_frame == _begin + _end. */
+int tf_integrate_frame_begin(tf_map* m, int32_t frame_index, int use_color, const tf_pose* pose, const tf_camera* cam,
+                             tf_chunk_id* ids_out, uint8_t* is_new_out, uint8_t* updated_out, float* quality_out,
+                             int64_t cap);
+int tf_integrate_frame_end(tf_map* m, tf_frame_stats* stats_out);
+
 /* Loop-closure path (GCFusion/MobileFusion.cpp:301-310): one item = one
  * ReIntegrateKeyframe call (:114-221).  flag 0: de-integrate the key-frame and its local
  * frames with their old poses over `ids` (= kf.validChunks).  flag 1: Prepare with the

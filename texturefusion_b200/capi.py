@@ -21,7 +21,7 @@ EXPORTS = [
     "tf_create", "tf_destroy", "tf_last_error", "tf_reset", "tf_set_truncation", "tf_host_alloc", "tf_host_free",
     "tf_upload_frame", "tf_upload_keyframe_rgb", "tf_release_frame", "tf_frame_device_ptrs",
     "tf_comm_unique_id", "tf_comm_init", "tf_broadcast_frame",
-    "tf_prepare", "tf_integrate", "tf_integrate_group", "tf_remove_chunks", "tf_integrate_frame",
+    "tf_prepare", "tf_integrate", "tf_integrate_group", "tf_remove_chunks", "tf_integrate_frame", "tf_integrate_frame_begin", "tf_integrate_frame_end",
     "tf_integrate_batch", "tf_mesh_chunks", "tf_has_chunk", "tf_chunk_count", "tf_list_chunks", "tf_download_chunks",
     "tf_atlas_alloc_slot", "tf_atlas_update", "tf_atlas_download", "tf_atlas_patch_size", "tf_patch_texcoords", "tf_sync", "tf_wait_upload",
     "tf_get_counters", "tf_stream", "tf_copy_stream", "tf_set_profiling", "tf_get_kernel_time", "tf_get_stage_times", "tf_debug_project",
@@ -119,6 +119,8 @@ def load() -> C.CDLL:
     L.tf_remove_chunks.argtypes = [vp, vp, i64]
     L.tf_integrate_frame.argtypes = [vp, C.c_int32, C.c_int, C.POINTER(Pose), C.POINTER(Camera),
                                      C.POINTER(FrameStats), vp, vp, vp, vp, i64]
+    L.tf_integrate_frame_begin.argtypes = [vp, C.c_int32, C.c_int, C.POINTER(Pose), C.POINTER(Camera), vp, vp, vp, vp, i64]
+    L.tf_integrate_frame_end.argtypes = [vp, C.POINTER(FrameStats)]
     L.tf_integrate_batch.argtypes = [vp, C.POINTER(BatchItem), i64, C.POINTER(Camera)]
     L.tf_has_chunk.argtypes = [vp, ChunkId]
     L.tf_chunk_count.argtypes = [vp]

@@ -42,7 +42,7 @@ struct FrameSlot {
   unsigned char* valid = nullptr;
   cudaEvent_t ready = nullptr;  // recorded on the copy stream after the slot's uploads
   bool pending = false;         // uploads in flight: consumers on the compute stream wait for `ready`
-  bool read_by_compute = false; // kernels that read the slot were queued since its last upload
+  uint64_t read_ticket = 0;     // ticket of the last queued compute work that reads the slot (0: none since its upload)
   bool pinned = false;          // key-frame rgb kept for the atlas: not evictable until tf_release_frame
 };
 
@@ -111,6 +111,7 @@ struct tf_map {
   cudaStream_t stream = nullptr;       // all kernels and read-backs
   cudaStream_t copy_stream = nullptr;  // frame uploads: the next frame's H2D copy overlaps the current frame's kernels
   cudaEvent_t reuse_ev = nullptr;      // orders an overwriting upload behind the kernels that read the slot
+  uint64_t compute_ticket = 0, compute_done = 0;  // see guard_overwrite
   cudaEvent_t patch_copy_done = nullptr;  // tf_atlas_update: the descriptor copy has left the page-locked arena
   std::string err;
   unsigned char* slab = nullptr;        // frame store: per slot [depth | rgba | quality | rgb | valid], contiguous so
@@ -185,6 +186,19 @@ struct tf_map {
   int pool_next = 0;
   int parity = 0;  // which set of bounding-box accumulators the current frame uses
   tf_counters counters{};
+
+  // a fused frame that has been launched but not collected (tf_integrate_frame_begin / _end)
+  struct PendingFrame {
+    bool active = false, graph = false;
+    unsigned seq = 0;
+    int n_frames = 0, ocap = 0;
+    bool color[kMaxGroupFrames] = {};
+    tf_chunk_id* ids_out = nullptr;
+    uint8_t *new_out = nullptr, *upd_out = nullptr;
+    float* q_out = nullptr;
+    bool direct[4] = {false, false, false, false};
+    uint64_t ticket = 0;
+  } pend;
 
   // CUDA graphs of the fused per-frame chain, one per (colour, group size); see fused_group
   FrameGraph graphs[2][2][kMaxGroupFrames + 1];  // [lists exported][colour][group size]
@@ -286,7 +300,7 @@ int find_slot(tf_map* m, int32_t frame_index, bool for_compute = true) {
   FrameSlot& fsl = m->slots[it->second];
   fsl.last_use = ++m->use_clock;
   if (for_compute) {
-    fsl.read_by_compute = true;
+    fsl.read_ticket = ++m->compute_ticket;
     if (fsl.pending) {
       cudaStreamWaitEvent(m->stream, fsl.ready, 0);
       fsl.pending = false;
@@ -297,11 +311,13 @@ int find_slot(tf_map* m, int32_t frame_index, bool for_compute = true) {
 
 // Before the copy stream overwrites a slot that queued kernels may still be reading (a re-upload
 // of the same index, or a slot taken over from an evicted frame): order the copy behind them.
+// (Work up to ticket compute_done is known to have finished — the host has collected its results —
+//  so in the streaming loop, where frame i+1 is uploaded while frame i runs, the copy is not held back.)
 void guard_overwrite(tf_map* m, FrameSlot& fsl) {
-  if (!fsl.read_by_compute) return;
+  if (fsl.read_ticket <= m->compute_done) return;
   cudaEventRecord(m->reuse_ev, m->stream);
   cudaStreamWaitEvent(m->copy_stream, m->reuse_ev, 0);
-  fsl.read_by_compute = false;
+  fsl.read_ticket = 0;
 }
 
 // Slot for frame_index: existing, free, or the least-recently-used one that is not pinned
@@ -757,6 +773,7 @@ int tf_sync(tf_map* m) {
   use_device(m);
   CUDA_OK(m, cudaStreamSynchronize(m->copy_stream));
   CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  if (!m->pend.active) m->compute_done = m->compute_ticket;
   prof_collect(m, 0);
   return TF_OK;
 }
@@ -1135,12 +1152,12 @@ static int wait_frame(tf_map* m, unsigned seq) {
 }
 
 // Shared body of the fused pipelines: prepare on frames[0], integrate the group, finalize.
-static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, const tf_camera* cam,
-                       tf_frame_stats* stats, tf_chunk_id* ids_out, uint8_t* new_out, uint8_t* upd_out,
-                       float* q_out, int64_t cap) {
+static int fused_group_begin(tf_map* m, const tf_group_frame* frames, int n_frames, const tf_camera* cam,
+                             tf_chunk_id* ids_out, uint8_t* new_out, uint8_t* upd_out, float* q_out, int64_t cap) {
   HT(0);
+  if (m->pend.active) return fail(m, TF_ERR_INVALID, "a fused frame is already in flight (call tf_integrate_frame_end first)");
   FrameArgs a;
-  bool color[kMaxGroupFrames];
+  bool* color = m->pend.color;
   if (int rc = build_group(m, frames, n_frames, cam, a.gp, color)) return rc;
   const int s = find_slot(m, frames[0].frame_index);
   make_cull_params(m->cfg.voxel_res, m->cfg.trunc, m->cfg.dot3_order, frames[0].pose, *cam, a.cp);
@@ -1195,7 +1212,6 @@ static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, co
     a.parity = m->parity;
     if (int rc = launch_frame_graph(m, fg, a)) return rc;
     HT(5);
-    if (int rc = wait_frame(m, ff.seq)) return rc;
     launched = true;
   }
   if (!launched) {  // plain launches (profiling with events between the stages, or graphs unavailable)
@@ -1207,8 +1223,35 @@ static int fused_group(tf_map* m, const tf_group_frame* frames, int n_frames, co
       if (int rc = check_kernel(m, "export_kernel")) return rc;
     }
     HT(5);
+  }
+  tf_map::PendingFrame& pf = m->pend;
+  pf.active = true;
+  pf.ticket = m->compute_ticket;
+  pf.graph = launched;
+  pf.seq = ff.seq;
+  pf.n_frames = n_frames;
+  pf.ocap = ocap;
+  pf.ids_out = ids_out, pf.new_out = new_out, pf.upd_out = upd_out, pf.q_out = q_out;
+  for (int k = 0; k < 4; k++) pf.direct[k] = direct[k] != nullptr;
+  return TF_OK;
+}
+
+static int fused_group_end(tf_map* m, tf_frame_stats* stats) {
+  tf_map::PendingFrame& pf = m->pend;
+  if (!pf.active) return fail(m, TF_ERR_INVALID, "tf_integrate_frame_end: no fused frame in flight");
+  pf.active = false;
+  if (pf.graph) {
+    if (int rc = wait_frame(m, pf.seq)) return rc;
+  } else {
     CUDA_OK(m, cudaStreamSynchronize(m->stream));
   }
+  m->compute_done = std::max(m->compute_done, pf.ticket);
+  const bool* color = pf.color;
+  const int n_frames = pf.n_frames, ocap = pf.ocap;
+  tf_chunk_id* ids_out = pf.ids_out;
+  uint8_t *new_out = pf.new_out, *upd_out = pf.upd_out;
+  float* q_out = pf.q_out;
+  const bool* direct = pf.direct;
   HT(6);
   absorb_result(m);
   const FrameResultHost r = *m->res_h;
@@ -1242,7 +1285,27 @@ int tf_integrate_frame(tf_map* m, int32_t frame_index, int use_color, const tf_p
   g.flag = 1;
   g.reserved = 0;
   g.pose = *pose;
-  return fused_group(m, &g, 1, cam, stats, ids_out, is_new_out, updated_out, quality_out, cap);
+  if (int rc = fused_group_begin(m, &g, 1, cam, ids_out, is_new_out, updated_out, quality_out, cap)) return rc;
+  return fused_group_end(m, stats);
+}
+
+int tf_integrate_frame_begin(tf_map* m, int32_t frame_index, int use_color, const tf_pose* pose, const tf_camera* cam,
+                             tf_chunk_id* ids_out, uint8_t* is_new_out, uint8_t* updated_out, float* quality_out, int64_t cap) {
+  if (!m || !pose || !cam_ok(m, cam) || cap < 0) return fail(m, TF_ERR_INVALID, "tf_integrate_frame_begin: bad argument");
+  use_device(m);
+  tf_group_frame g;
+  g.frame_index = frame_index;
+  g.use_color = use_color;
+  g.flag = 1;
+  g.reserved = 0;
+  g.pose = *pose;
+  return fused_group_begin(m, &g, 1, cam, ids_out, is_new_out, updated_out, quality_out, cap);
+}
+
+int tf_integrate_frame_end(tf_map* m, tf_frame_stats* stats_out) {
+  if (!m) return TF_ERR_INVALID;
+  use_device(m);
+  return fused_group_end(m, stats_out);
 }
 
 // ---- loop-closure batches ---------------------------------------------------------------------------
@@ -1282,6 +1345,7 @@ static int flush_batch(tf_map* m, std::vector<PendingItem>& pend) {
   publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);  // error bits and allocator state of the whole sub-batch
   if (int rc = check_kernel(m, "publish_kernel")) return rc;
   CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  m->compute_done = m->compute_ticket;
   absorb_result(m);
   const int dev_err = m->res_h->error;
   int rc = TF_OK;

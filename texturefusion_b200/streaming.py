@@ -1,11 +1,12 @@
 """The streaming loop of the fusion path as a caller writes it against the C ABI — shared by
 bench.py's end-to-end leg and the multi-process parity test, so that what is timed is what is tested.
 
-Single GPU:   upload(i+1) | fuse(i) | wait_upload(i+1)            (double buffered, page-locked sources)
-N GPUs:       rank 0 uploads frame i+1; every rank calls tf_broadcast_frame(i+1) — ONE ncclBroadcast
-              inside the library, queued on the upload stream behind the copy —; every rank fuses
-              frame i into its shard of the chunks; tf_wait_upload(i+1) closes the step.
-All arguments are marshalled once; a step is three C calls and no Python glue in between.
+Single GPU:   fuse_begin(i) | upload(i+1) | fuse_end(i) | wait_upload(i+1)   (double buffered, page-locked sources)
+N GPUs:       every rank queues frame i on its shard (tf_integrate_frame_begin); rank 0 uploads frame
+              i+1; every rank calls tf_broadcast_frame(i+1) — ONE ncclBroadcast inside the library, queued
+              on the upload stream behind the copy —; tf_integrate_frame_end(i) collects the frame's
+              lists; tf_wait_upload(i+1) closes the step.
+All arguments are marshalled once; a step is four or five C calls and no Python glue in between.
 """
 from __future__ import annotations
 
@@ -60,18 +61,25 @@ class FrameStreamer:
         if self.world > 1:
             self._ok(self.L.tf_broadcast_frame(self.m.h, fr.index, int(fr.is_keyframe), 0))
 
-    def fuse(self, i):
+    def fuse_begin(self, i):
         fr = self.frames[i]
         vp = C.c_void_p
         if self.want_lists:
-            rc = self.L.tf_integrate_frame(self.m.h, fr.index, int(fr.is_keyframe), C.byref(self.poses[i]), C.byref(self.camc),
-                                           C.byref(self.st), vp(self.out_ids.ptr), vp(self.out_new.ptr), vp(self.out_upd.ptr),
-                                           vp(self.out_q.ptr), self.cap)
+            rc = self.L.tf_integrate_frame_begin(self.m.h, fr.index, int(fr.is_keyframe), C.byref(self.poses[i]), C.byref(self.camc),
+                                                 vp(self.out_ids.ptr), vp(self.out_new.ptr), vp(self.out_upd.ptr),
+                                                 vp(self.out_q.ptr), self.cap)
         else:
-            rc = self.L.tf_integrate_frame(self.m.h, fr.index, int(fr.is_keyframe), C.byref(self.poses[i]), C.byref(self.camc),
-                                           C.byref(self.st), None, None, None, None, 0)
+            rc = self.L.tf_integrate_frame_begin(self.m.h, fr.index, int(fr.is_keyframe), C.byref(self.poses[i]), C.byref(self.camc),
+                                                 None, None, None, None, 0)
         self._ok(rc)
+
+    def fuse_end(self):
+        self._ok(self.L.tf_integrate_frame_end(self.m.h, C.byref(self.st)))
         return self.st.n_chunks
+
+    def fuse(self, i):
+        self.fuse_begin(i)
+        return self.fuse_end()
 
     def wait(self, i):
         self._ok(self.L.tf_wait_upload(self.m.h, self.frames[i].index))
@@ -80,8 +88,9 @@ class FrameStreamer:
         """One end-to-end step for frame i (frame i must have been staged): next frame's ingest in
         flight during this frame's kernels and finished inside the step."""
         j = (i + 1) % self.nf
-        self.stage(j)
-        n = self.fuse(i)
+        self.fuse_begin(i)  # frame i's kernels are running ...
+        self.stage(j)       # ... while the host queues frame i+1's copy (+ broadcast)
+        n = self.fuse_end()
         self.wait(j)
         return n
 
