@@ -343,7 +343,7 @@ def main():
     e2e_step = fs.step
 
     k = 0
-    fs.stage(0)
+    fs.prime(0)
     m.sync()
     for _ in range(args.warmup):
         e2e_step(k % nf)

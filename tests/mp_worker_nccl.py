@@ -37,13 +37,10 @@ def main():
     m = capi.Map(args.res, device=local_rank, n_ranks=world, rank=rank, max_frames=8, max_chunks=1 << 18)
     m.comm_init(capi.share_unique_id(dist, dev))
     fs = FrameStreamer(m, frames, cam, rank=rank, world=world, cap=1 << 17)
-    fs.stage(0)
+    fs.prime(0)
     per_frame = []
     for i in range(args.frames):
-        if i + 1 < args.frames:
-            fs.step(i)
-        else:  # last frame: nothing left to stage
-            fs.fuse(i)
+        fs.step(i)  # (the frames staged past the end wrap around to the first ones and are never fused)
         per_frame.append(fs.lists())
     m.sync()
     ids, hashes = sorted_chunk_hashes(m)

@@ -6,6 +6,10 @@ N GPUs:       every rank queues frame i on its shard (tf_integrate_frame_begin);
               i+1; every rank calls tf_broadcast_frame(i+1) — ONE ncclBroadcast inside the library, queued
               on the upload stream behind the copy —; tf_integrate_frame_end(i) collects the frame's
               lists; tf_wait_upload(i+1) closes the step.
+              With N > 1 the ingest runs TWO frames ahead (`lookahead`): NCCL's broadcast kernel needs an
+              SM slot, and integrate_kernel occupies every SM while it runs, so a broadcast queued one
+              frame ahead would only start when the frame's kernels end and then sit on the critical path
+              of the next frame; queued two ahead it runs in the bbox / culling phase of the frame between.
 All arguments are marshalled once; a step is four or five C calls and no Python glue in between.
 """
 from __future__ import annotations
@@ -18,8 +22,9 @@ from . import capi
 
 
 class FrameStreamer:
-    def __init__(self, m: capi.Map, frames, cam, *, rank=0, world=1, cap=1 << 16, want_lists=True):
+    def __init__(self, m: capi.Map, frames, cam, *, rank=0, world=1, cap=1 << 16, want_lists=True, lookahead=None):
         self.m, self.frames, self.cam, self.rank, self.world = m, frames, cam, rank, world
+        self.lookahead = lookahead or (2 if world > 1 else 1)
         self.L = m.L
         self.nf = len(frames)
         self.camc = capi.make_camera(cam)
@@ -84,14 +89,18 @@ class FrameStreamer:
     def wait(self, i):
         self._ok(self.L.tf_wait_upload(self.m.h, self.frames[i].index))
 
+    def prime(self, i):
+        """Stage the frames a first step(i) expects to be on their way: i .. i + lookahead - 1."""
+        for k in range(self.lookahead):
+            self.stage((i + k) % self.nf)
+
     def step(self, i):
-        """One end-to-end step for frame i (frame i must have been staged): next frame's ingest in
-        flight during this frame's kernels and finished inside the step."""
-        j = (i + 1) % self.nf
-        self.fuse_begin(i)  # frame i's kernels are running ...
-        self.stage(j)       # ... while the host queues frame i+1's copy (+ broadcast)
+        """One end-to-end step for frame i (frames i .. i+lookahead-1 have been staged): one frame's ingest
+        is queued while this frame's kernels run, and the NEXT frame to be fused has arrived when the step ends."""
+        self.fuse_begin(i)                           # frame i's kernels are running ...
+        self.stage((i + self.lookahead) % self.nf)   # ... while the host queues a later frame's copy (+ broadcast)
         n = self.fuse_end()
-        self.wait(j)
+        self.wait((i + 1) % self.nf)
         return n
 
     def lists(self):
