@@ -25,14 +25,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=32)
     ap.add_argument("--res", type=float, default=0.005)
-    ap.add_argument("--start", type=int, default=0)
+    ap.add_argument("--first-frame", type=int, default=0)
     args = ap.parse_args()
     rank, local_rank, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
     dist.init_process_group("nccl", device_id=torch.device(dev))
     cam = synth.Camera()
-    seq = synth.make_sequence(args.frames, cam=cam, total=300, keyframe_every=10, device=dev, start=args.start)
+    seq = synth.make_sequence(args.frames, cam=cam, total=300, keyframe_every=10, device=dev, start=args.first_frame)
     frames = seq.frames
     m = capi.Map(args.res, device=local_rank, n_ranks=world, rank=rank, max_frames=8, max_chunks=1 << 18)
     m.comm_init(capi.share_unique_id(dist, dev))

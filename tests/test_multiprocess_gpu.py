@@ -31,4 +31,4 @@ def test_two_rank_nccl_stream_equals_cpu_reference():
 
 @pytest.mark.skipif(_gpus() < 4, reason="needs 4 GPUs")
 def test_four_rank_nccl_stream_equals_cpu_reference():
-    run_workers(4, ["--frames", "22", "--res", "0.005", "--start", "100"])
+    run_workers(4, ["--frames", "22", "--res", "0.005", "--first-frame", "100"])
