@@ -751,3 +751,66 @@ def test_maps_on_two_devices_in_one_process():
     for k, m in enumerate(maps):
         assert assert_maps_equal(m, o, what=f"map on device {k}")
         m.close()
+
+
+def test_reupload_replaces_the_slot_and_keyframes_stay_pinned():
+    """(a) re-uploading a frame index WITHOUT colour / quality must not leave the previous
+    upload's planes marked valid (the reference reads NULL as "no colour" / quality 0); (b) key-frames
+    uploaded with tf_upload_keyframe_rgb are not evicted by later uploads; (c) an upload that overwrites
+    a slot is ordered behind queued kernels that read it."""
+    seq = room_sequence(6)
+    cam = seq.cam
+    kf, lf = seq.frames[0], seq.frames[1]
+    g = capi.Map(0.02, max_frames=3)
+    o = OracleMap(0.02)
+    SCR = 77
+    # key-frame with colour + quality, then the same index re-uploaded depth-only
+    g.upload_frame(SCR, kf.depth, kf.rgba(), kf.quality)
+    ids, new = g.prepare(SCR, kf.pose, cam)
+    oi, on = o.prepare(kf.depth, kf.pose, cam)
+    assert np.array_equal(ids, oi)
+    nu, q = g.integrate(SCR, True, kf.pose, cam, ids, 1)
+    ou, oq = o.integrate(kf.depth, kf.rgba(), kf.quality, kf.pose, cam, oi, 1, kf.index)
+    assert np.array_equal(nu, ou) and np.array_equal(q.view(np.uint32), oq.view(np.uint32))
+    g.upload_frame(SCR, lf.depth)  # no colour, no quality
+    with pytest.raises(capi.TexFusionError) as e:  # asking for colour now must fail, not use the stale plane
+        g.integrate(SCR, True, lf.pose, cam, ids, 1)
+    assert e.value.code == capi.TF_ERR_NOT_FOUND
+    nu, q = g.integrate(SCR, False, lf.pose, cam, ids, 1, nu)
+    ou, _ = o.integrate(lf.depth, None, None, lf.pose, cam, oi, 1, -1, ou)
+    assert np.array_equal(nu, ou)
+    # colour without a quality plane: the sums must be those of a NULL observationQualityPointer (0 / sentinel), not stale data
+    g.upload_frame(SCR, kf.depth, kf.rgba(), None)
+    nu2, q2 = g.integrate(SCR, True, kf.pose, cam, ids, 1)
+    ou2, oq2 = o.integrate(kf.depth, kf.rgba(), None, kf.pose, cam, oi, 1, kf.index)
+    assert np.array_equal(q2.view(np.uint32), oq2.view(np.uint32))
+    assert_maps_equal(g, o, what="re-upload protocol")
+    # (b) pinned key-frames survive later uploads; the store refuses when only pinned slots remain
+    p = capi.Map(0.02, max_frames=3)
+    for k in (0, 1):
+        p.upload_frame(100 + k, kf.depth)
+        p.upload_keyframe_rgb(100 + k, kf.rgb)
+    for k in range(5):  # all of these share the one evictable slot
+        p.upload_frame(k, lf.depth)
+    loc = p.atlas_alloc_slot((0, 0, 0))
+    p.atlas_update([(loc, 100, 10, 10, 8, 8), (p.atlas_alloc_slot((1, 0, 0)), 101, 20, 20, 8, 8)])  # both key-frames still there
+    p.upload_frame(102, kf.depth)
+    p.upload_keyframe_rgb(102, kf.rgb)  # third pinned slot: nothing evictable left
+    with pytest.raises(capi.TexFusionError) as e:
+        p.upload_frame(7, lf.depth)
+    assert e.value.code == capi.TF_ERR_CAPACITY
+    p.release_frame(100)
+    p.upload_frame(7, lf.depth)
+    # (c) overwrite ordering: queue a fused frame asynchronously, overwrite its slot at once, collect
+    s = capi.Map(0.02, max_frames=2)
+    s2 = OracleMap(0.02)
+    import ctypes as C
+    s.upload_frame(1, kf.depth)
+    st = capi.FrameStats()
+    assert s.L.tf_integrate_frame_begin(s.h, 1, 0, C.byref(capi.make_pose(kf.pose)), C.byref(capi.make_camera(cam)), None, None,
+                                        None, None, 0) == 0
+    s.upload_frame(1, np.zeros_like(kf.depth))  # must wait for the kernels that read slot 1
+    assert s.L.tf_integrate_frame_end(s.h, C.byref(st)) == 0
+    n, n_upd = s2.integrate_frame(kf.depth, None, None, kf.pose, cam, -1)
+    assert (st.n_chunks, st.n_updated) == (n, n_upd)
+    assert_maps_equal(s, s2, what="overwrite during an in-flight frame")
