@@ -1690,24 +1690,30 @@ int tf_atlas_update(tf_map* m, const tf_patch_desc* patches, int64_t n) {
   if (int rc = ensure_arena_bytes(m, m->ar_patch_d, (size_t)n * sizeof(PatchDev))) return rc;
   if (m->patch_copy_done) cudaEventSynchronize(m->patch_copy_done);  // the previous call's H2D copy has left the host arena
   PatchDev* pd = (PatchDev*)m->ar_patch_h.p;
+  int last_fi = -1, s = -1;  // patches arrive grouped by key-frame: one frame-store lookup per run
   for (int64_t i = 0; i < n; i++) {
     const tf_patch_desc& p = patches[i];
-    const int s = find_slot(m, p.frame_index);
+    if (p.frame_index != last_fi || s < 0) {
+      s = find_slot(m, p.frame_index);
+      last_fi = p.frame_index;
+    }
     if (s < 0 || !m->slots[s].has_rgb) return fail(m, TF_ERR_NOT_FOUND, "tf_atlas_update: key-frame rgb not in the frame store");
+    if (p.texloc >= (uint64_t)kAtlasDim * kAtlasDim) return fail(m, TF_ERR_INVALID, "tf_atlas_update: texloc outside the atlas");
     if (p.w <= 0 || p.h <= 0 || p.x < 0 || p.y < 0 || p.x + p.w > m->W || p.y + p.h > m->H)
       return fail(m, TF_ERR_INVALID, "tf_atlas_update: bbox outside the image");
     const int ox = (int)(p.texloc % kAtlasDim), oy = (int)(p.texloc / kAtlasDim);
     const bool shrink = p.w > m->patch_w || p.h > m->patch_h;
     const int ew = shrink ? m->patch_w : p.w, eh = shrink ? m->patch_h : p.h;
     if (ox + ew > kAtlasDim || oy + eh > kAtlasDim) return fail(m, TF_ERR_INVALID, "tf_atlas_update: slot outside the atlas");
-    pd[i] = PatchDev{p.texloc, m->slots[s].rgb, p.x, p.y, p.w, p.h};
+    pd[i] = PatchDev{(unsigned)p.texloc, (unsigned short)s, (unsigned short)p.x, (unsigned short)p.y, (unsigned short)p.w,
+                     (unsigned short)p.h, 0};
   }
   CUDA_OK(m, cudaMemcpyAsync(m->ar_patch_d.p, pd, (size_t)n * sizeof(PatchDev), cudaMemcpyHostToDevice, m->stream));
   if (!m->patch_copy_done) CUDA_OK(m, cudaEventCreateWithFlags(&m->patch_copy_done, cudaEventDisableTiming));
   CUDA_OK(m, cudaEventRecord(m->patch_copy_done, m->stream));
   const int grid = (int)std::min<int64_t>((n + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)m->sm_count * 8);
-  atlas_update_kernel<<<grid, kThreads, 0, m->stream>>>((const PatchDev*)m->ar_patch_d.p, (int)n, m->atlas, m->W, m->H, m->patch_w,
-                                                        m->patch_h);
+  atlas_update_kernel<<<grid, kThreads, 0, m->stream>>>((const PatchDev*)m->ar_patch_d.p, (int)n, m->atlas, m->slots[0].rgb,
+                                                        m->slot_stride, m->W, m->H, m->patch_w, m->patch_h);
   if (int rc = check_kernel(m, "atlas_update_kernel")) return rc;
   m->counters.h2d_bytes += n * (int64_t)sizeof(PatchDev);
   return TF_OK;
