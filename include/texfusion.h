@@ -296,6 +296,40 @@ int tf_patch_texcoords(tf_map* m, int32_t frame_index, const tf_pose* world_to_c
                        int64_t n_patches, const int64_t* vertex_offsets, const float* vertices,
                        const float* colors, float* texcoord_out, float* texcolor_out, tf_patch_result* results);
 
+/* ---- frame pre-processing ------------------------------------------------
+ * The per-pixel loops that the reference runs between loading a frame and fusing it
+ * (main.cpp:117-147), on the planes of the frame store; they replace
+ *   BasicAPI::extractNormalMapSIMD      BasicAPI.cpp:849-905   -> tf_pre_normal_map
+ *   BasicAPI::refineKeyframesSIMD       BasicAPI.cpp:506-636   -> tf_pre_refine_keyframe
+ *   BasicAPI::refineNewframesSIMD       BasicAPI.cpp:378-442   -> tf_pre_refine_newframe
+ *   BasicAPI::refineDepthUseNormalSIMD  BasicAPI.cpp:728-780   -> tf_pre_refine_depth_by_normal
+ *   BasicAPI::checkColorQuality + estimateColorQuality (:783-847) and the RGBA pack of
+ *   GCFusion/MobileFusion.cpp:151-162                          -> tf_pre_color_quality
+ * A frame enters with tf_upload_frame(depth only: Frame::refined_depth after framePreprocess); a
+ * key-frame then needs ONE more upload, its 3-byte RGB, instead of the RGBA, colour-valid and
+ * quality planes.  The calls are asynchronous (queued on the ingest stream behind the upload; the
+ * fusion calls wait for them like for an upload).
+ * `cam` carries the camera's FLOAT intrinsics as main.cpp passes them (camera.c_fx ...): they are
+ * NOT truncated to integers here (near_plane / far_plane are ignored).  Transforms are 3x4 row-major
+ * [R | t] in float: ref_to_new = (new.pose_sophus[0].inverse() * ref.pose_sophus[0]).matrix().block<3,4>(0,0)
+ * cast to float (BasicAPI.cpp:529-538), new_to_ref the inverse product (:395-399).
+ * Per frame the library keeps a normal map (3 planes) and the refinement weights (Frame::weight,
+ * zero for a new upload) for the four most recently touched frames.
+ * Where the reference leaves memory unwritten (cv::Mat::create: the normal map's border, colour flags
+ * of rejected pixels) the planes are 0.  _mm256_rsqrt_ps is reproduced from the instruction's value
+ * table (Intel), see texturefusion_b200/csrc/tf_rsqrt_table.h.  Requires width % 8 == 0. */
+int tf_pre_normal_map(tf_map* m, int32_t frame_index, const tf_camera* cam);
+int tf_pre_refine_keyframe(tf_map* m, int32_t keyframe_index, int32_t new_index, const float* ref_to_new, const tf_camera* cam);
+int tf_pre_refine_newframe(tf_map* m, int32_t keyframe_index, int32_t new_index, const float* new_to_ref, const tf_camera* cam);
+int tf_pre_refine_depth_by_normal(tf_map* m, int32_t frame_index, const tf_camera* cam);
+/* rgb: Frame::rgb (host, H x W x 3).  Fills the key-frame's colour-valid, quality and RGBA planes and keeps the rgb
+ * for the atlas (the slot is pinned like after tf_upload_keyframe_rgb). */
+int tf_pre_color_quality(tf_map* m, int32_t frame_index, const uint8_t* rgb, const tf_camera* cam);
+/* Read-back for the tracker and for parity (blocking; any pointer may be NULL): refined depth, normal map
+ * (3 planes: x | y | z), refinement weights, colour-valid flags, quality. */
+int tf_pre_download(tf_map* m, int32_t frame_index, float* depth, float* normal, float* weight, uint8_t* color_valid,
+                    float* quality);
+
 /* ---- misc ---------------------------------------------------------------------------- */
 int tf_sync(tf_map* m);
 /* Blocks until the uploads of one stored frame have completed (its page-locked source buffers may

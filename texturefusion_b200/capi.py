@@ -24,6 +24,8 @@ EXPORTS = [
     "tf_prepare", "tf_integrate", "tf_integrate_group", "tf_remove_chunks", "tf_integrate_frame", "tf_integrate_frame_begin", "tf_integrate_frame_end",
     "tf_integrate_batch", "tf_mesh_chunks", "tf_has_chunk", "tf_chunk_count", "tf_list_chunks", "tf_download_chunks",
     "tf_atlas_alloc_slot", "tf_atlas_update", "tf_atlas_download", "tf_atlas_patch_size", "tf_patch_texcoords", "tf_sync", "tf_wait_upload",
+    "tf_pre_normal_map", "tf_pre_refine_keyframe", "tf_pre_refine_newframe", "tf_pre_refine_depth_by_normal", "tf_pre_color_quality",
+    "tf_pre_download",
     "tf_get_counters", "tf_stream", "tf_copy_stream", "tf_set_profiling", "tf_get_kernel_time", "tf_get_stage_times", "tf_debug_project",
 ]
 
@@ -133,6 +135,13 @@ def load() -> C.CDLL:
     L.tf_atlas_download.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
     L.tf_atlas_patch_size.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.tf_patch_texcoords.argtypes = [vp, C.c_int32, C.POINTER(Pose), C.POINTER(Camera), i64, vp, vp, vp, vp, vp, vp]
+    camp = C.POINTER(Camera)
+    L.tf_pre_normal_map.argtypes = [vp, C.c_int32, camp]
+    L.tf_pre_refine_keyframe.argtypes = [vp, C.c_int32, C.c_int32, vp, camp]
+    L.tf_pre_refine_newframe.argtypes = [vp, C.c_int32, C.c_int32, vp, camp]
+    L.tf_pre_refine_depth_by_normal.argtypes = [vp, C.c_int32, camp]
+    L.tf_pre_color_quality.argtypes = [vp, C.c_int32, vp, camp]
+    L.tf_pre_download.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
     L.tf_sync.argtypes = [vp]
     L.tf_wait_upload.argtypes = [vp, C.c_int32]
     L.tf_get_counters.argtypes = [vp, C.POINTER(Counters)]
@@ -465,6 +474,43 @@ class Map:
         self._check(self.L.tf_patch_texcoords(self.h, frame_index, C.byref(make_pose(world_to_camera)),
                                               C.byref(make_camera(cam)), n, _p(off), _p(v), _p(c), _p(tc), _p(col), _p(res)))
         return tc, col, res[:n]
+
+    # frame pre-processing (BasicAPI.cpp loops on the frame store) --------------------------------
+    def pre_normal_map(self, frame_index, cam):
+        self._check(self.L.tf_pre_normal_map(self.h, frame_index, C.byref(make_camera(cam))))
+
+    def pre_refine_keyframe(self, keyframe_index, new_index, ref_to_new, cam):
+        T = np.ascontiguousarray(np.asarray(ref_to_new)[:3, :4], np.float32)
+        self._check(self.L.tf_pre_refine_keyframe(self.h, keyframe_index, new_index, _p(T), C.byref(make_camera(cam))))
+
+    def pre_refine_newframe(self, keyframe_index, new_index, new_to_ref, cam):
+        T = np.ascontiguousarray(np.asarray(new_to_ref)[:3, :4], np.float32)
+        self._check(self.L.tf_pre_refine_newframe(self.h, keyframe_index, new_index, _p(T), C.byref(make_camera(cam))))
+
+    def pre_refine_depth_by_normal(self, frame_index, cam):
+        self._check(self.L.tf_pre_refine_depth_by_normal(self.h, frame_index, C.byref(make_camera(cam))))
+
+    def pre_color_quality(self, frame_index, rgb, cam):
+        c = np.ascontiguousarray(rgb, np.uint8)
+        self._check(self.L.tf_pre_color_quality(self.h, frame_index, _p(c), C.byref(make_camera(cam))))
+        self._keep = c  # (the copy is asynchronous)
+
+    def pre_download(self, frame_index, *, depth=False, normal=False, weight=False, color_valid=False, quality=False) -> dict:
+        H, W = self.height, self.width
+        out = {}
+        if depth:
+            out["depth"] = np.empty((H, W), np.float32)
+        if normal:
+            out["normal"] = np.empty((3, H, W), np.float32)
+        if weight:
+            out["weight"] = np.empty((H, W), np.float32)
+        if color_valid:
+            out["color_valid"] = np.empty((H, W), np.uint8)
+        if quality:
+            out["quality"] = np.empty((H, W), np.float32)
+        g = lambda k: _p(out[k]) if k in out else None  # noqa: E731
+        self._check(self.L.tf_pre_download(self.h, frame_index, g("depth"), g("normal"), g("weight"), g("color_valid"), g("quality")))
+        return out
 
     # misc -----------------------------------------------------------------------------------
     def sync(self):

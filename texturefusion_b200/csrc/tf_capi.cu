@@ -24,6 +24,7 @@
 #include "tf_host_math.h"
 #include "tf_kernels.cuh"
 #include "tf_mesh.cuh"
+#include "tf_pre.cuh"
 
 using namespace tfb;
 
@@ -180,6 +181,15 @@ struct tf_map {
   struct Arena { void* p = nullptr; size_t cap = 0; bool host = false; };
   Arena ar_mesh_ids, ar_mesh_counts, ar_mesh_off, ar_mesh_v, ar_mesh_n, ar_mesh_c, ar_mesh_i, ar_mesh_off_h;
   Arena ar_tc_off, ar_tc_v, ar_tc_c, ar_tc_tc, ar_tc_col, ar_tc_res, ar_list, ar_patch_h, ar_patch_d;
+
+  // frame pre-processing (tf_pre_*): the side planes of the few frames being prepared (normal map, refinement
+  // weights; least-recently-used replacement) and the scratch of the in-place key-frame refinement
+  struct PreEntry { int frame_index = -1; float* normal = nullptr; float* weight = nullptr; bool has_normal = false; uint64_t last_use = 0; };
+  PreEntry pre[4];
+  float* pre_out_d = nullptr;
+  float* pre_out_w = nullptr;
+  int* pre_queue = nullptr;      // [npix] + the counter behind it
+  unsigned char* pre_waiting = nullptr;
 
   // host mirrors
   int64_t n_live = 0;
@@ -572,6 +582,8 @@ void tf_destroy(tf_map* m) {
   cudaFreeHost(m->res_h); cudaFreeHost(m->out_ids_h); cudaFreeHost(m->out_new_h); cudaFreeHost(m->out_upd_h);
   cudaFreeHost(m->out_q_h); cudaFreeHost(m->upd_stage_h); cudaFreeHost(m->q_stage_h);
   cudaFree(m->slab);
+  for (auto& e : m->pre) { cudaFree(e.normal); cudaFree(e.weight); }
+  cudaFree(m->pre_out_d); cudaFree(m->pre_out_w); cudaFree(m->pre_queue); cudaFree(m->pre_waiting);
   for (tf_map::Arena* a : {&m->ar_mesh_ids, &m->ar_mesh_counts, &m->ar_mesh_off, &m->ar_mesh_v, &m->ar_mesh_n, &m->ar_mesh_c,
                            &m->ar_mesh_i, &m->ar_mesh_off_h, &m->ar_tc_off, &m->ar_tc_v, &m->ar_tc_c, &m->ar_tc_tc,
                            &m->ar_tc_col, &m->ar_tc_res, &m->ar_list, &m->ar_patch_h, &m->ar_patch_d})
@@ -808,6 +820,8 @@ int tf_upload_frame(tf_map* m, int32_t frame_index, const float* depth, const ui
   // the planes of this upload replace the slot's contents: planes that are not passed are absent
   // afterwards (the reference reads NULL pointers as "no colour" / quality 0, Structure/Chisel.h:218-249)
   fsl.has_rgba = fsl.has_quality = fsl.has_rgb = false;
+  for (auto& e : m->pre)  // a fresh frame: no normal map yet, refinement weights 0 (framePreprocess, BasicAPI.cpp:942-953)
+    if (e.frame_index == frame_index) e.frame_index = -1;
   const size_t nb = (size_t)m->npix * 4;
   CUDA_OK(m, cudaMemcpyAsync(fsl.depth, depth, nb, cudaMemcpyHostToDevice, m->copy_stream));
   m->counters.h2d_bytes += nb;
@@ -1770,6 +1784,171 @@ int tf_patch_texcoords(tf_map* m, int32_t frame_index, const tf_pose* world_to_c
   CUDA_OK(m, cudaStreamSynchronize(m->stream));
   m->counters.h2d_bytes += nv * 24 + (n_patches + 1) * 8;
   m->counters.d2h_bytes += nv * 20 + n_patches * (int64_t)sizeof(PatchTexResult);
+  return TF_OK;
+}
+
+// ---- frame pre-processing (kernels in tf_pre.cuh) -----------------------------------
+//
+// The loops of main.cpp:117-147 on the planes of the frame store.  They are part of a frame's INGEST:
+// everything runs on the copy stream, behind the frame's upload, and re-arms the slot's `ready` event,
+// so the fusion kernels see the refined planes exactly as they would see an upload.
+
+namespace {
+
+bool pre_cam_ok(const tf_map* m, const tf_camera* c) {
+  return c && c->width == m->W && c->height == m->H && (m->W % 8) == 0 && c->fx != 0.0f && c->fy != 0.0f;
+}
+PreCam pre_cam(const tf_map* m, const tf_camera* c) { return PreCam{c->fx, c->fy, c->cx, c->cy, m->W, m->H, m->cfg.dot3_order}; }
+PreXf pre_xf(const float* T) {
+  PreXf x;
+  for (int a = 0; a < 3; a++) {
+    for (int b = 0; b < 3; b++) x.r[a][b] = T[a * 4 + b];
+    x.t[a] = T[a * 4 + 3];
+  }
+  return x;
+}
+
+// Side planes of a frame (created on first use: weights 0, no normal map).
+tf_map::PreEntry* pre_entry(tf_map* m, int frame_index, bool create) {
+  tf_map::PreEntry* lru = nullptr;  // a free entry, else the least recently used one
+  for (auto& e : m->pre) {
+    if (e.frame_index == frame_index) { e.last_use = ++m->use_clock; return &e; }
+    const bool e_free = e.frame_index < 0, l_free = lru && lru->frame_index < 0;
+    if (!lru || (e_free && !l_free) || (e_free == l_free && e.last_use < lru->last_use)) lru = &e;
+  }
+  if (!create) return nullptr;
+  if (!lru->normal) {
+    if (cudaMalloc(&lru->normal, (size_t)m->npix * 12) != cudaSuccess || cudaMalloc(&lru->weight, (size_t)m->npix * 4) != cudaSuccess) {
+      fail(m, TF_ERR_CUDA, "tf_pre: out of device memory");
+      return nullptr;
+    }
+  }
+  cudaMemsetAsync(lru->weight, 0, (size_t)m->npix * 4, m->copy_stream);
+  lru->frame_index = frame_index, lru->has_normal = false, lru->last_use = ++m->use_clock;
+  return lru;
+}
+
+int pre_scratch(tf_map* m) {
+  if (m->pre_out_d) return TF_OK;
+  CUDA_OK(m, cudaMalloc(&m->pre_out_d, (size_t)m->npix * 4));
+  CUDA_OK(m, cudaMalloc(&m->pre_out_w, (size_t)m->npix * 4));
+  CUDA_OK(m, cudaMalloc(&m->pre_queue, ((size_t)m->npix + 1) * 4));
+  CUDA_OK(m, cudaMalloc(&m->pre_waiting, (size_t)m->npix));
+  return TF_OK;
+}
+
+// The slot of a frame whose planes the copy stream is about to read (modify = false) or rewrite.
+int pre_slot(tf_map* m, int32_t frame_index, bool modify) {
+  const int s = find_slot(m, frame_index, false);
+  if (s < 0) { fail(m, TF_ERR_NOT_FOUND, "tf_pre: frame_index not in the frame store (tf_upload_frame first)"); return -1; }
+  if (modify) guard_overwrite(m, m->slots[s]);
+  return s;
+}
+int pre_publish(tf_map* m, FrameSlot& fsl) {  // the slot's planes changed: consumers wait for the copy stream again
+  CUDA_OK(m, cudaEventRecord(fsl.ready, m->copy_stream));
+  fsl.pending = true;
+  return TF_OK;
+}
+
+}  // namespace
+
+int tf_pre_normal_map(tf_map* m, int32_t frame_index, const tf_camera* cam) {
+  if (!m || !pre_cam_ok(m, cam)) return fail(m, TF_ERR_INVALID, "tf_pre_normal_map: bad argument");
+  use_device(m);
+  const int s = pre_slot(m, frame_index, false);
+  if (s < 0) return TF_ERR_NOT_FOUND;
+  tf_map::PreEntry* e = pre_entry(m, frame_index, true);
+  if (!e) return TF_ERR_CUDA;
+  pre_normal_kernel<<<m->grid, 256, 0, m->copy_stream>>>(pre_cam(m, cam), m->slots[s].depth, e->normal);
+  e->has_normal = true;
+  return check_kernel(m, "pre_normal_kernel");
+}
+
+int tf_pre_refine_depth_by_normal(tf_map* m, int32_t frame_index, const tf_camera* cam) {
+  if (!m || !pre_cam_ok(m, cam)) return fail(m, TF_ERR_INVALID, "tf_pre_refine_depth_by_normal: bad argument");
+  use_device(m);
+  tf_map::PreEntry* e = pre_entry(m, frame_index, false);
+  if (!e || !e->has_normal) return fail(m, TF_ERR_NOT_FOUND, "tf_pre_refine_depth_by_normal: no normal map (tf_pre_normal_map first)");
+  const int s = pre_slot(m, frame_index, true);
+  if (s < 0) return TF_ERR_NOT_FOUND;
+  pre_grazing_kernel<<<m->grid, 256, 0, m->copy_stream>>>(pre_cam(m, cam), e->normal, m->slots[s].depth);
+  if (int rc = check_kernel(m, "pre_grazing_kernel")) return rc;
+  return pre_publish(m, m->slots[s]);
+}
+
+int tf_pre_refine_keyframe(tf_map* m, int32_t keyframe_index, int32_t new_index, const float* ref_to_new, const tf_camera* cam) {
+  if (!m || !ref_to_new || !pre_cam_ok(m, cam) || keyframe_index == new_index)
+    return fail(m, TF_ERR_INVALID, "tf_pre_refine_keyframe: bad argument");
+  use_device(m);
+  const int sn = pre_slot(m, new_index, false);
+  const int sk = sn < 0 ? -1 : pre_slot(m, keyframe_index, true);
+  if (sk < 0) return TF_ERR_NOT_FOUND;
+  tf_map::PreEntry* e = pre_entry(m, keyframe_index, true);
+  if (!e) return TF_ERR_CUDA;
+  if (int rc = pre_scratch(m)) return rc;
+  RefineKfArgs a;
+  a.c = pre_cam(m, cam);
+  a.x = pre_xf(ref_to_new);
+  a.kf_d = m->slots[sk].depth, a.kf_w = e->weight, a.new_d = m->slots[sn].depth;
+  a.out_d = m->pre_out_d, a.out_w = m->pre_out_w;
+  a.queue = m->pre_queue, a.queue_n = m->pre_queue + m->npix, a.waiting = m->pre_waiting;
+  CUDA_OK(m, cudaMemsetAsync(a.queue_n, 0, 4, m->copy_stream));
+  pre_refine_kf_kernel<<<m->grid, 256, 0, m->copy_stream>>>(a);
+  if (int rc = check_kernel(m, "pre_refine_kf_kernel")) return rc;
+  pre_refine_kf_resolve_kernel<<<1, 1024, 0, m->copy_stream>>>(a);
+  if (int rc = check_kernel(m, "pre_refine_kf_resolve_kernel")) return rc;
+  CUDA_OK(m, cudaMemcpyAsync(m->slots[sk].depth, a.out_d, (size_t)m->npix * 4, cudaMemcpyDeviceToDevice, m->copy_stream));
+  CUDA_OK(m, cudaMemcpyAsync(e->weight, a.out_w, (size_t)m->npix * 4, cudaMemcpyDeviceToDevice, m->copy_stream));
+  return pre_publish(m, m->slots[sk]);
+}
+
+int tf_pre_refine_newframe(tf_map* m, int32_t keyframe_index, int32_t new_index, const float* new_to_ref, const tf_camera* cam) {
+  if (!m || !new_to_ref || !pre_cam_ok(m, cam) || keyframe_index == new_index)
+    return fail(m, TF_ERR_INVALID, "tf_pre_refine_newframe: bad argument");
+  use_device(m);
+  const int sk = pre_slot(m, keyframe_index, false);
+  const int sn = sk < 0 ? -1 : pre_slot(m, new_index, true);
+  if (sn < 0) return TF_ERR_NOT_FOUND;
+  pre_refine_new_kernel<<<m->grid, 256, 0, m->copy_stream>>>(pre_cam(m, cam), pre_xf(new_to_ref), m->slots[sk].depth, m->slots[sn].depth);
+  if (int rc = check_kernel(m, "pre_refine_new_kernel")) return rc;
+  return pre_publish(m, m->slots[sn]);
+}
+
+int tf_pre_color_quality(tf_map* m, int32_t frame_index, const uint8_t* rgb, const tf_camera* cam) {
+  if (!m || !rgb || !pre_cam_ok(m, cam)) return fail(m, TF_ERR_INVALID, "tf_pre_color_quality: bad argument");
+  use_device(m);
+  tf_map::PreEntry* e = pre_entry(m, frame_index, false);
+  if (!e || !e->has_normal) return fail(m, TF_ERR_NOT_FOUND, "tf_pre_color_quality: no normal map (tf_pre_normal_map first)");
+  const int s = pre_slot(m, frame_index, true);
+  if (s < 0) return TF_ERR_NOT_FOUND;
+  FrameSlot& fsl = m->slots[s];
+  if (int rc = ensure_color_planes(m, fsl)) return rc;
+  fsl.pinned = true;  // as tf_upload_keyframe_rgb: the key-frame's rgb stays for the atlas until tf_release_frame
+  CUDA_OK(m, cudaMemcpyAsync(fsl.rgb, rgb, (size_t)m->npix * 3, cudaMemcpyHostToDevice, m->copy_stream));
+  m->counters.h2d_bytes += (int64_t)m->npix * 3;
+  pre_color_kernel<<<m->grid, 256, 0, m->copy_stream>>>(pre_cam(m, cam), fsl.depth, e->normal, fsl.rgb, fsl.valid, fsl.quality, fsl.rgba);
+  if (int rc = check_kernel(m, "pre_color_kernel")) return rc;
+  fsl.has_rgb = fsl.has_rgba = fsl.has_quality = true;
+  return pre_publish(m, fsl);
+}
+
+int tf_pre_download(tf_map* m, int32_t frame_index, float* depth, float* normal, float* weight, uint8_t* color_valid, float* quality) {
+  if (!m) return TF_ERR_INVALID;
+  use_device(m);
+  const int s = pre_slot(m, frame_index, false);
+  if (s < 0) return TF_ERR_NOT_FOUND;
+  FrameSlot& fsl = m->slots[s];
+  tf_map::PreEntry* e = pre_entry(m, frame_index, false);
+  if ((normal && !(e && e->has_normal)) || (weight && !e)) return fail(m, TF_ERR_NOT_FOUND, "tf_pre_download: plane not computed for this frame");
+  if ((color_valid || quality) && !(fsl.has_rgb && fsl.has_quality)) return fail(m, TF_ERR_NOT_FOUND, "tf_pre_download: no colour planes for this frame");
+  const size_t n = (size_t)m->npix;
+  if (depth) CUDA_OK(m, cudaMemcpyAsync(depth, fsl.depth, n * 4, cudaMemcpyDeviceToHost, m->copy_stream));
+  if (normal) CUDA_OK(m, cudaMemcpyAsync(normal, e->normal, n * 12, cudaMemcpyDeviceToHost, m->copy_stream));
+  if (weight) CUDA_OK(m, cudaMemcpyAsync(weight, e->weight, n * 4, cudaMemcpyDeviceToHost, m->copy_stream));
+  if (color_valid) CUDA_OK(m, cudaMemcpyAsync(color_valid, fsl.valid, n, cudaMemcpyDeviceToHost, m->copy_stream));
+  if (quality) CUDA_OK(m, cudaMemcpyAsync(quality, fsl.quality, n * 4, cudaMemcpyDeviceToHost, m->copy_stream));
+  CUDA_OK(m, cudaStreamSynchronize(m->copy_stream));
+  m->counters.d2h_bytes += (int64_t)n * ((depth ? 4 : 0) + (normal ? 12 : 0) + (weight ? 4 : 0) + (color_valid ? 1 : 0) + (quality ? 4 : 0));
   return TF_OK;
 }
 
