@@ -37,4 +37,6 @@ def _built():
     build_oracle()
     build_ref()  # no-op without /root/reference (the GPU box uses the prebuilt oracle/_ref)
     build_library()
+    from oracle import pre
+    pre.build()
     yield

@@ -186,9 +186,8 @@ struct tf_map {
   // weights; least-recently-used replacement) and the scratch of the in-place key-frame refinement
   struct PreEntry { int frame_index = -1; float* normal = nullptr; float* weight = nullptr; bool has_normal = false; uint64_t last_use = 0; };
   PreEntry pre[4];
-  float* pre_out_d = nullptr;
-  float* pre_out_w = nullptr;
-  int* pre_queue = nullptr;      // [npix] + the counter behind it
+  float* pre_snap = nullptr;     // snapshot of the key-frame's depth
+  int* pre_queue = nullptr;      // [npix] + counter + last-block ticket
   unsigned char* pre_waiting = nullptr;
 
   // host mirrors
@@ -583,7 +582,7 @@ void tf_destroy(tf_map* m) {
   cudaFreeHost(m->out_q_h); cudaFreeHost(m->upd_stage_h); cudaFreeHost(m->q_stage_h);
   cudaFree(m->slab);
   for (auto& e : m->pre) { cudaFree(e.normal); cudaFree(e.weight); }
-  cudaFree(m->pre_out_d); cudaFree(m->pre_out_w); cudaFree(m->pre_queue); cudaFree(m->pre_waiting);
+  cudaFree(m->pre_snap); cudaFree(m->pre_queue); cudaFree(m->pre_waiting);
   for (tf_map::Arena* a : {&m->ar_mesh_ids, &m->ar_mesh_counts, &m->ar_mesh_off, &m->ar_mesh_v, &m->ar_mesh_n, &m->ar_mesh_c,
                            &m->ar_mesh_i, &m->ar_mesh_off_h, &m->ar_tc_off, &m->ar_tc_v, &m->ar_tc_c, &m->ar_tc_tc,
                            &m->ar_tc_col, &m->ar_tc_res, &m->ar_list, &m->ar_patch_h, &m->ar_patch_d})
@@ -1829,10 +1828,10 @@ tf_map::PreEntry* pre_entry(tf_map* m, int frame_index, bool create) {
 }
 
 int pre_scratch(tf_map* m) {
-  if (m->pre_out_d) return TF_OK;
-  CUDA_OK(m, cudaMalloc(&m->pre_out_d, (size_t)m->npix * 4));
-  CUDA_OK(m, cudaMalloc(&m->pre_out_w, (size_t)m->npix * 4));
-  CUDA_OK(m, cudaMalloc(&m->pre_queue, ((size_t)m->npix + 1) * 4));
+  if (m->pre_snap) return TF_OK;
+  CUDA_OK(m, cudaMalloc(&m->pre_snap, (size_t)m->npix * 4));
+  CUDA_OK(m, cudaMalloc(&m->pre_queue, ((size_t)m->npix + 2) * 4));
+  CUDA_OK(m, cudaMemsetAsync(m->pre_queue + m->npix, 0, 8, m->copy_stream));
   CUDA_OK(m, cudaMalloc(&m->pre_waiting, (size_t)m->npix));
   return TF_OK;
 }
@@ -1889,16 +1888,14 @@ int tf_pre_refine_keyframe(tf_map* m, int32_t keyframe_index, int32_t new_index,
   RefineKfArgs a;
   a.c = pre_cam(m, cam);
   a.x = pre_xf(ref_to_new);
-  a.kf_d = m->slots[sk].depth, a.kf_w = e->weight, a.new_d = m->slots[sn].depth;
-  a.out_d = m->pre_out_d, a.out_w = m->pre_out_w;
-  a.queue = m->pre_queue, a.queue_n = m->pre_queue + m->npix, a.waiting = m->pre_waiting;
+  a.kf_d = m->pre_snap, a.kf_w = e->weight, a.new_d = m->slots[sn].depth;
+  a.out_d = m->slots[sk].depth, a.out_w = e->weight;
+  a.queue = m->pre_queue, a.queue_n = m->pre_queue + m->npix, a.ticket = (unsigned*)(m->pre_queue + m->npix + 1);
+  a.waiting = m->pre_waiting;
+  CUDA_OK(m, cudaMemcpyAsync(m->pre_snap, m->slots[sk].depth, (size_t)m->npix * 4, cudaMemcpyDeviceToDevice, m->copy_stream));
   CUDA_OK(m, cudaMemsetAsync(a.queue_n, 0, 4, m->copy_stream));
   pre_refine_kf_kernel<<<m->grid, 256, 0, m->copy_stream>>>(a);
   if (int rc = check_kernel(m, "pre_refine_kf_kernel")) return rc;
-  pre_refine_kf_resolve_kernel<<<1, 1024, 0, m->copy_stream>>>(a);
-  if (int rc = check_kernel(m, "pre_refine_kf_resolve_kernel")) return rc;
-  CUDA_OK(m, cudaMemcpyAsync(m->slots[sk].depth, a.out_d, (size_t)m->npix * 4, cudaMemcpyDeviceToDevice, m->copy_stream));
-  CUDA_OK(m, cudaMemcpyAsync(e->weight, a.out_w, (size_t)m->npix * 4, cudaMemcpyDeviceToDevice, m->copy_stream));
   return pre_publish(m, m->slots[sk]);
 }
 

@@ -107,19 +107,20 @@ __global__ void __launch_bounds__(256) pre_grazing_kernel(const PreCam c, float*
 // The reference updates the key-frame IN PLACE, eight pixels per step in raster order, and its
 // nearest sample reads the KEY-FRAME's own depth (:597-600) at the new frame's pixel position: a step
 // that reads a position written by an earlier step sees the UPDATED value.  Here every pixel is
-// computed from the old plane into a second plane; the few pixels whose nearest sample lies in an
-// earlier 8-pixel step are queued and resolved in dependency order by pre_refine_kf_resolve_kernel
-// (a pixel's source is always earlier in raster order, so the queue drains), then the planes are swapped back.
+// computed from a snapshot of the old plane straight into the key-frame's plane; the few pixels whose
+// nearest sample lies in an earlier 8-pixel step are queued and resolved in dependency order by the
+// last block to finish (a pixel's source is always earlier in raster order, so the queue drains).
 struct RefineKfArgs {
   PreCam c;
   PreXf x;              // key-frame camera -> new camera
-  const float* kf_d;    // old key-frame depth
-  const float* kf_w;    // old weights
+  const float* kf_d;    // snapshot of the key-frame's depth before this call
+  const float* kf_w;    // weights (each pixel reads and writes only its own: updated in place, kf_w == out_w)
   const float* new_d;   // new frame's depth
-  float* out_d;         // updated depth
-  float* out_w;         // updated weights
+  float* out_d;         // the key-frame's depth plane
+  float* out_w;
   int* queue;           // pixels waiting for an updated nearest sample
   int* queue_n;
+  unsigned* ticket;     // last-block election (resets itself)
   unsigned char* waiting;  // per pixel: 1 while queued
 };
 
@@ -153,7 +154,7 @@ __device__ __forceinline__ int refine_kf_pixel(const RefineKfArgs& a, int p, boo
       const int qn = __float2int_rn(floorf(u + 0.5f) + floorf(v + 0.5f) * (float)c.W);
       const bool earlier = (qn >> 3) < (p >> 3);  // written by an earlier 8-pixel step (W is a multiple of 8)
       if (earlier && !use_new) return qn;
-      nearest = earlier ? a.out_d[qn] : a.kf_d[qn];
+      nearest = earlier ? __ldcg(a.out_d + qn) : a.kf_d[qn];  // (updated plane: written by other blocks, read through L2)
     }
     bil = nearest;
   }
@@ -171,16 +172,13 @@ __global__ void __launch_bounds__(256) pre_refine_kf_kernel(const RefineKfArgs a
   const int np = a.c.W * a.c.H;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
     const int src = refine_kf_pixel(a, p, false);
-    if (src >= 0) {
-      a.waiting[p] = 1;
-      a.queue[atomicAdd(a.queue_n, 1)] = p;
-    }
+    a.waiting[p] = src >= 0;
+    if (src >= 0) a.queue[atomicAdd(a.queue_n, 1)] = p;
   }
-}
-
-// One block.  Round by round: a queued pixel whose nearest sample is no longer waiting is computed.
-__global__ void __launch_bounds__(1024) pre_refine_kf_resolve_kernel(const RefineKfArgs a) {
-  const int n = *a.queue_n;
+  if (!last_block_done(a.ticket)) return;
+  // ---- last block: the queued pixels, round by round; a pixel whose nearest sample is no longer waiting is computed
+  const int n = *(volatile int*)a.queue_n;
+  if (n == 0) return;
   for (;;) {
     int left = 0;
     // (1) decide on the flags as they stand at the start of the round
@@ -188,20 +186,19 @@ __global__ void __launch_bounds__(1024) pre_refine_kf_resolve_kernel(const Refin
       const int p = a.queue[k];
       if (p < 0) continue;
       const int src = refine_kf_pixel(a, p, false);  // (re-derives the sample position: cheaper than storing it)
-      if (a.waiting[src]) {
+      if (__ldcg(a.waiting + src)) {
         left++;
         continue;
       }
-      a.queue[k] = -(p + 2);  // ready: resolved in step (2)
+      a.queue[k] = -(p + 2);  // ready: computed in step (2)
     }
     __syncthreads();
     // (2) compute the ready pixels from the updated plane
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
       const int e = a.queue[k];
       if (e >= -1) continue;
-      const int p = -e - 2;
-      refine_kf_pixel(a, p, true);
-      a.waiting[p] = 0;
+      refine_kf_pixel(a, -e - 2, true);
+      a.waiting[-e - 2] = 0;
       a.queue[k] = -1;
     }
     if (__syncthreads_count(left) == 0) break;
