@@ -318,6 +318,15 @@ int tf_patch_texcoords(tf_map* m, int32_t frame_index, const tf_pose* world_to_c
  * Where the reference leaves memory unwritten (cv::Mat::create: the normal map's border, colour flags
  * of rejected pixels) the planes are 0.  _mm256_rsqrt_ps is reproduced from the instruction's value
  * table (Intel), see texturefusion_b200/csrc/tf_rsqrt_table.h.  Requires width % 8 == 0. */
+/* framePreprocess (Tools/DatasetWrapper.hpp:187-263, BasicAPI.cpp:942-1004), optional: the raw 16-bit depth image
+ * instead of tf_upload_frame's float plane (values above max_depth * depth_scale are dropped, then
+ * metres = value / depth_scale), and cv::bilateralFilter(refined_depth, d, sigma_color, sigma_space) — the reference
+ * calls it with (9, 0.03, 10) — restated from OpenCV's float path (4096-bin exp table with interpolation,
+ * disc of radius d/2, BORDER_REFLECT_101).  The filter agrees with cv2 to float rounding (accumulation order), not
+ * bit for bit: a caller that needs the reference's exact refined depth keeps cv::bilateralFilter on the host and
+ * uses tf_upload_frame. */
+int tf_pre_upload_depth_u16(tf_map* m, int32_t frame_index, const uint16_t* depth, float depth_scale, float max_depth);
+int tf_pre_bilateral(tf_map* m, int32_t frame_index, int32_t d, float sigma_color, float sigma_space);
 int tf_pre_normal_map(tf_map* m, int32_t frame_index, const tf_camera* cam);
 int tf_pre_refine_keyframe(tf_map* m, int32_t keyframe_index, int32_t new_index, const float* ref_to_new, const tf_camera* cam);
 int tf_pre_refine_newframe(tf_map* m, int32_t keyframe_index, int32_t new_index, const float* new_to_ref, const tf_camera* cam);

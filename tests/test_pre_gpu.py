@@ -182,3 +182,36 @@ def test_errors():
     G.m.upload_frame(f, np.ones((480, 640), np.float32), None, None)
     with pytest.raises(capi.TexFusionError):
         G.m.pre_refine_depth_by_normal(f, cam)
+
+
+def test_raw_depth_conversion_and_bilateral_filter():
+    """framePreprocess: 16-bit depth -> metres with the range cut (bit-exact), then cv::bilateralFilter(9, 0.03, 10)
+    against cv2 — OpenCV's own accumulation order is SIMD-width dependent, so the bar is float rounding:
+    2e-6 relative (stated in include/texfusion.h)."""
+    cv2 = pytest.importorskip("cv2")
+    cam = synth.Camera()
+    fr = synth.make_sequence(1, cam=cam, total=300, keyframe_every=10).frames[0]
+    rng = np.random.default_rng(4)
+    metres = fr.depth + np.where(fr.depth > 0, rng.normal(0, 0.003, fr.depth.shape), 0).astype(np.float32)
+    raw = np.clip(np.round(metres * 1000.0), 0, 65535).astype(np.uint16)
+    raw[100:110, 200:260] = 9000  # beyond max_depth = 5 m: dropped
+    G = GpuPre(cam.width, cam.height)
+    G.m.pre_upload_depth_u16(1, raw, 1000.0, 5.0)
+    got = G.m.pre_download(1, depth=True)["depth"]
+    r = raw.copy()
+    r[r.astype(np.float32) > np.float32(5.0) * np.float32(1000.0)] = 0
+    want = r.astype(np.float32) / np.float32(1000.0)
+    assert eq(got, want) and (want[100:110, 200:260] == 0).all()
+    for (d, sc, ss) in ((9, 0.03, 10.0), (9, 0.03, 4.5), (7, 0.03, 10.0)):
+        G.m.pre_upload_depth_u16(2, raw, 1000.0, 5.0)
+        G.m.pre_bilateral(2, d, sc, ss)
+        g = G.m.pre_download(2, depth=True)["depth"]
+        w = cv2.bilateralFilter(want, d, sc, ss)
+        err = np.abs(g - w) / np.maximum(np.abs(w), 1e-3)
+        assert err.max() < 2e-6, (d, sc, ss, float(err.max()))
+        assert np.abs(g - want).max() > 1e-4  # the filter did something
+    # a constant image is copied
+    flat = np.full((cam.height, cam.width), 1.25, np.float32)
+    G.m.upload_frame(3, flat)
+    G.m.pre_bilateral(3)
+    assert eq(G.m.pre_download(3, depth=True)["depth"], flat)

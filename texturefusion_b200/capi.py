@@ -24,7 +24,7 @@ EXPORTS = [
     "tf_prepare", "tf_integrate", "tf_integrate_group", "tf_remove_chunks", "tf_integrate_frame", "tf_integrate_frame_begin", "tf_integrate_frame_end",
     "tf_integrate_batch", "tf_mesh_chunks", "tf_has_chunk", "tf_chunk_count", "tf_list_chunks", "tf_download_chunks",
     "tf_atlas_alloc_slot", "tf_atlas_update", "tf_atlas_download", "tf_atlas_patch_size", "tf_patch_texcoords", "tf_sync", "tf_wait_upload",
-    "tf_pre_normal_map", "tf_pre_refine_keyframe", "tf_pre_refine_newframe", "tf_pre_refine_depth_by_normal", "tf_pre_color_quality",
+    "tf_pre_upload_depth_u16", "tf_pre_bilateral", "tf_pre_normal_map", "tf_pre_refine_keyframe", "tf_pre_refine_newframe", "tf_pre_refine_depth_by_normal", "tf_pre_color_quality",
     "tf_pre_download",
     "tf_get_counters", "tf_stream", "tf_copy_stream", "tf_set_profiling", "tf_get_kernel_time", "tf_get_stage_times", "tf_debug_project",
 ]
@@ -137,6 +137,8 @@ def load() -> C.CDLL:
     L.tf_patch_texcoords.argtypes = [vp, C.c_int32, C.POINTER(Pose), C.POINTER(Camera), i64, vp, vp, vp, vp, vp, vp]
     camp = C.POINTER(Camera)
     L.tf_pre_normal_map.argtypes = [vp, C.c_int32, camp]
+    L.tf_pre_upload_depth_u16.argtypes = [vp, C.c_int32, vp, C.c_float, C.c_float]
+    L.tf_pre_bilateral.argtypes = [vp, C.c_int32, C.c_int32, C.c_float, C.c_float]
     L.tf_pre_refine_keyframe.argtypes = [vp, C.c_int32, C.c_int32, vp, camp]
     L.tf_pre_refine_newframe.argtypes = [vp, C.c_int32, C.c_int32, vp, camp]
     L.tf_pre_refine_depth_by_normal.argtypes = [vp, C.c_int32, camp]
@@ -476,6 +478,14 @@ class Map:
         return tc, col, res[:n]
 
     # frame pre-processing (BasicAPI.cpp loops on the frame store) --------------------------------
+    def pre_upload_depth_u16(self, frame_index, depth_u16, depth_scale, max_depth):
+        d = np.ascontiguousarray(depth_u16, np.uint16)
+        self._check(self.L.tf_pre_upload_depth_u16(self.h, frame_index, _p(d), depth_scale, max_depth))
+        self._keep = d  # (the copy is asynchronous)
+
+    def pre_bilateral(self, frame_index, d=9, sigma_color=0.03, sigma_space=10.0):
+        self._check(self.L.tf_pre_bilateral(self.h, frame_index, d, sigma_color, sigma_space))
+
     def pre_normal_map(self, frame_index, cam):
         self._check(self.L.tf_pre_normal_map(self.h, frame_index, C.byref(make_camera(cam))))
 

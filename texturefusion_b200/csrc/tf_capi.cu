@@ -186,7 +186,8 @@ struct tf_map {
   // weights; least-recently-used replacement) and the scratch of the in-place key-frame refinement
   struct PreEntry { int frame_index = -1; float* normal = nullptr; float* weight = nullptr; bool has_normal = false; uint64_t last_use = 0; };
   PreEntry pre[4];
-  float* pre_snap = nullptr;     // snapshot of the key-frame's depth
+  float* pre_snap = nullptr;     // snapshot of the key-frame's depth / staging of a raw 16-bit depth image
+  BilateralState* pre_bil = nullptr;
   int* pre_queue = nullptr;      // [npix] + counter + last-block ticket
   unsigned char* pre_waiting = nullptr;
 
@@ -582,7 +583,7 @@ void tf_destroy(tf_map* m) {
   cudaFreeHost(m->out_q_h); cudaFreeHost(m->upd_stage_h); cudaFreeHost(m->q_stage_h);
   cudaFree(m->slab);
   for (auto& e : m->pre) { cudaFree(e.normal); cudaFree(e.weight); }
-  cudaFree(m->pre_snap); cudaFree(m->pre_queue); cudaFree(m->pre_waiting);
+  cudaFree(m->pre_snap); cudaFree(m->pre_bil); cudaFree(m->pre_queue); cudaFree(m->pre_waiting);
   for (tf_map::Arena* a : {&m->ar_mesh_ids, &m->ar_mesh_counts, &m->ar_mesh_off, &m->ar_mesh_v, &m->ar_mesh_n, &m->ar_mesh_c,
                            &m->ar_mesh_i, &m->ar_mesh_off_h, &m->ar_tc_off, &m->ar_tc_v, &m->ar_tc_c, &m->ar_tc_tc,
                            &m->ar_tc_col, &m->ar_tc_res, &m->ar_list, &m->ar_patch_h, &m->ar_patch_d})
@@ -1830,6 +1831,7 @@ tf_map::PreEntry* pre_entry(tf_map* m, int frame_index, bool create) {
 int pre_scratch(tf_map* m) {
   if (m->pre_snap) return TF_OK;
   CUDA_OK(m, cudaMalloc(&m->pre_snap, (size_t)m->npix * 4));
+  CUDA_OK(m, cudaMalloc(&m->pre_bil, sizeof(BilateralState)));
   CUDA_OK(m, cudaMalloc(&m->pre_queue, ((size_t)m->npix + 2) * 4));
   CUDA_OK(m, cudaMemsetAsync(m->pre_queue + m->npix, 0, 8, m->copy_stream));
   CUDA_OK(m, cudaMalloc(&m->pre_waiting, (size_t)m->npix));
@@ -1850,6 +1852,50 @@ int pre_publish(tf_map* m, FrameSlot& fsl) {  // the slot's planes changed: cons
 }
 
 }  // namespace
+
+int tf_pre_upload_depth_u16(tf_map* m, int32_t frame_index, const uint16_t* depth, float depth_scale, float max_depth) {
+  if (!m || !depth || frame_index < 0 || !(depth_scale > 0.0f)) return fail(m, TF_ERR_INVALID, "tf_pre_upload_depth_u16: bad argument");
+  use_device(m);
+  if (int rc = pre_scratch(m)) return rc;
+  const int s = acquire_slot(m, frame_index);
+  if (s < 0) return TF_ERR_CAPACITY;
+  FrameSlot& fsl = m->slots[s];
+  guard_overwrite(m, fsl);
+  fsl.has_rgba = fsl.has_quality = fsl.has_rgb = false;
+  for (auto& e : m->pre)
+    if (e.frame_index == frame_index) e.frame_index = -1;
+  CUDA_OK(m, cudaMemcpyAsync(m->pre_snap, depth, (size_t)m->npix * 2, cudaMemcpyHostToDevice, m->copy_stream));
+  m->counters.h2d_bytes += (int64_t)m->npix * 2;
+  pre_depth_u16_kernel<<<m->grid, 256, 0, m->copy_stream>>>((const unsigned short*)m->pre_snap, fsl.depth, m->npix, depth_scale, max_depth);
+  if (int rc = check_kernel(m, "pre_depth_u16_kernel")) return rc;
+  return pre_publish(m, fsl);
+}
+
+int tf_pre_bilateral(tf_map* m, int32_t frame_index, int32_t d, float sigma_color, float sigma_space) {
+  if (!m) return TF_ERR_INVALID;
+  use_device(m);
+  // cv::bilateralFilter's parameter rules (sigma <= 0 -> 1; d <= 0 -> radius from sigma_space; radius >= 1)
+  if (sigma_color <= 0.0f) sigma_color = 1.0f;
+  if (sigma_space <= 0.0f) sigma_space = 1.0f;
+  int radius = d <= 0 ? (int)lrint(sigma_space * 1.5) : d / 2;
+  radius = std::max(radius, 1);
+  if (radius > kBilMaxRadius) return fail(m, TF_ERR_INVALID, "tf_pre_bilateral: diameter above 17 not supported");
+  if (int rc = pre_scratch(m)) return rc;
+  const int s = pre_slot(m, frame_index, true);
+  if (s < 0) return TF_ERR_NOT_FOUND;
+  FrameSlot& fsl = m->slots[s];
+  const double gc = -0.5 / ((double)sigma_color * sigma_color), gs = -0.5 / ((double)sigma_space * sigma_space);
+  static const int init[2] = {0x7fffffff, (int)0x80000000};  // (static: the copy is asynchronous)
+  CUDA_OK(m, cudaMemcpyAsync(m->pre_bil, init, 8, cudaMemcpyHostToDevice, m->copy_stream));
+  CUDA_OK(m, cudaMemcpyAsync(m->pre_snap, fsl.depth, (size_t)m->npix * 4, cudaMemcpyDeviceToDevice, m->copy_stream));
+  pre_minmax_kernel<<<m->grid, 256, 0, m->copy_stream>>>(m->pre_snap, m->npix, m->pre_bil);
+  if (int rc = check_kernel(m, "pre_minmax_kernel")) return rc;
+  pre_bilateral_lut_kernel<<<1, 1024, 0, m->copy_stream>>>(m->pre_bil, gc);
+  if (int rc = check_kernel(m, "pre_bilateral_lut_kernel")) return rc;
+  pre_bilateral_kernel<<<dim3((m->W + 31) / 32, (m->H + 7) / 8), 256, 0, m->copy_stream>>>(m->pre_snap, fsl.depth, m->W, m->H, radius, gs, m->pre_bil);
+  if (int rc = check_kernel(m, "pre_bilateral_kernel")) return rc;
+  return pre_publish(m, fsl);
+}
 
 int tf_pre_normal_map(tf_map* m, int32_t frame_index, const tf_camera* cam) {
   if (!m || !pre_cam_ok(m, cam)) return fail(m, TF_ERR_INVALID, "tf_pre_normal_map: bad argument");

@@ -253,4 +253,100 @@ __global__ void __launch_bounds__(256) pre_color_kernel(const PreCam c, const fl
   }
 }
 
+
+// ---- framePreprocess (Tools/DatasetWrapper.hpp:187-263; BasicAPI.cpp:942-1004) ------------------------
+// Raw sensor depth -> metres: values beyond the camera's range are dropped (:213-221).
+__global__ void __launch_bounds__(256) pre_depth_u16_kernel(const unsigned short* __restrict__ in, float* __restrict__ out, int np,
+                                                            float depth_scale, float max_depth) {
+  const float limit = max_depth * depth_scale;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+    unsigned short v = in[p];
+    if ((float)v > limit) v = 0;
+    out[p] = (float)v / depth_scale;
+  }
+}
+
+// cv::bilateralFilter on a CV_32FC1 image (:228-230: d = 9, sigmaColor = 0.03, sigmaSpace = 10), restated from
+// OpenCV's float path: range weights from a 4096-bin table of exp() over [0, max - min] with linear
+// interpolation, space weights exp(-r^2 / 2 sigma^2) on the disc r <= d/2, BORDER_REFLECT_101, the centre
+// tap added with weight 1.  OpenCV accumulates in float in its own (SIMD-width dependent) order, so
+// this agrees with cv2 to float rounding (tests: <= 2e-6 relative), not bit for bit.
+constexpr int kBilateralBins = 1 << 12;
+struct BilateralState {  // device scratch: [0] encoded min, [1] encoded max (ordered-int floats), then the table
+  int enc_min, enc_max;
+  float scale_index;
+  int flat;  // |max - min| < FLT_EPSILON: the filter is a copy
+  float lut[kBilateralBins + 2];
+};
+__global__ void __launch_bounds__(256) pre_minmax_kernel(const float* __restrict__ src, int np, BilateralState* st) {
+  float lo = 3.0e38f, hi = -3.0e38f;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+    const float v = src[p];
+    lo = fminf(lo, v), hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) lo = fminf(lo, __shfl_xor_sync(kFull, lo, d)), hi = fmaxf(hi, __shfl_xor_sync(kFull, hi, d));
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&st->enc_min, enc_f(lo));
+    atomicMax(&st->enc_max, enc_f(hi));
+  }
+}
+__global__ void __launch_bounds__(1024) pre_bilateral_lut_kernel(BilateralState* st, double gauss_color_coeff) {
+  const float mn = dec_f(st->enc_min), mx = dec_f(st->enc_max);
+  const float len = (float)((double)mx - (double)mn);
+  const float scale_index = (float)kBilateralBins / len;
+  if (threadIdx.x == 0) {
+    st->scale_index = scale_index;
+    st->flat = fabs((double)mn - (double)mx) < 1.1920928955078125e-7 ? 1 : 0;
+  }
+  for (int i = threadIdx.x; i < kBilateralBins + 2; i += blockDim.x) {
+    const double val = (double)((float)i / scale_index);
+    st->lut[i] = (float)exp(val * val * gauss_color_coeff);
+  }
+}
+constexpr int kBilMaxRadius = 8;
+__global__ void __launch_bounds__(256) pre_bilateral_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, int radius,
+                                                            double gauss_space_coeff, const BilateralState* __restrict__ st) {
+  // block = 32 x 8 pixels; the tile with its halo is staged in shared memory
+  __shared__ float tile[8 + 2 * kBilMaxRadius][32 + 2 * kBilMaxRadius + 1];
+  __shared__ float sw[(2 * kBilMaxRadius + 1) * (2 * kBilMaxRadius + 1)];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+  const int tw = 32 + 2 * radius, th = 8 + 2 * radius, side = 2 * radius + 1;
+  for (int k = threadIdx.x; k < tw * th; k += 256) {
+    const int lx = k % tw, ly = k / tw;
+    int gx = x0 + lx - radius, gy = y0 + ly - radius;
+    gx = gx < 0 ? -gx : (gx >= W ? 2 * W - 2 - gx : gx);  // BORDER_REFLECT_101
+    gy = gy < 0 ? -gy : (gy >= H ? 2 * H - 2 - gy : gy);
+    gx = min(max(gx, 0), W - 1), gy = min(max(gy, 0), H - 1);  // (tiles beyond the image: clamped, never used)
+    tile[ly][lx] = src[gy * W + gx];
+  }
+  for (int k = threadIdx.x; k < side * side; k += 256) {
+    const int i = k / side - radius, j = k % side - radius;
+    const double r = sqrt((double)i * i + (double)j * j);
+    sw[k] = (r > radius || (i == 0 && j == 0)) ? -1.0f : (float)exp(r * r * gauss_space_coeff);
+  }
+  __syncthreads();
+  const int x = x0 + tx, y = y0 + ty;
+  if (x >= W || y >= H) return;
+  const float val0 = tile[ty + radius][tx + radius];
+  if (st->flat) { dst[y * W + x] = val0; return; }
+  const float scale_index = st->scale_index;
+  float sum = 0.0f, wsum = 0.0f;
+  for (int i = 0; i < side; i++)
+    for (int j = 0; j < side; j++) {
+      const float kw = sw[i * side + j];
+      if (kw < 0.0f) continue;
+      const float rval = tile[ty + i][tx + j];
+      float alpha = fabsf(rval - val0) * scale_index;
+      const int idx = (int)floorf(alpha);
+      alpha -= (float)idx;
+      const float l0 = __ldg(st->lut + idx), l1 = __ldg(st->lut + idx + 1);
+      const float w = kw * (l0 + alpha * (l1 - l0));
+      wsum += w;
+      sum += rval * w;
+    }
+  dst[y * W + x] = (sum + val0) / (wsum + 1.0f);
+}
+
 }  // namespace tfb
