@@ -54,14 +54,17 @@ def main():
     st = capi.FrameStats()
     npix = cam.width * cam.height
     pins = [(capi.PinnedBuffer((npix,), np.float32), capi.PinnedBuffer((npix * 4,), np.uint8), capi.PinnedBuffer((npix,), np.float32))
-            for _ in range(2)] if rank == 0 else None
+            for _ in range(3)] if rank == 0 else None
+    # sharded maps ingest two frames ahead (see texturefusion_b200/streaming.py: the broadcast needs an SM slot
+    # and gets one in the bbox / culling phase of the frame in between)
+    ahead = 2 if world > 1 else 1
 
     def render(k):  # rank 0 only
         pose = synth.walk_pose(k, args.total)
         kf = k % 10 == 0
         depth, rgb, q = synth.render(pose, cam, color=kf, device=dev, scene="building")
         fr = synth.Frame(k, pose, depth, rgb, np.ones(depth.shape, np.uint8) if kf else None, q, kf)
-        d, c, qq = pins[k & 1]
+        d, c, qq = pins[k % 3]
         d.array[:] = np.asarray(fr.depth, np.float32).ravel()
         if kf:
             c.array[:] = np.asarray(fr.rgba(), np.uint8).ravel()
@@ -70,7 +73,7 @@ def main():
     def stage(k):
         kf = k % 10 == 0
         if rank == 0:
-            d, c, qq = pins[k & 1]
+            d, c, qq = pins[k % 3]
             rc = L.tf_upload_frame(m.h, k, vp(d.ptr), vp(c.ptr) if kf else None, vp(qq.ptr) if kf else None)
             assert rc == 0, L.tf_last_error(m.h)
         if world > 1:
@@ -83,19 +86,21 @@ def main():
         torch.cuda.synchronize()
 
     rows = []
-    if rank == 0:
-        render(0)
-    stage(0)
+    for j in range(min(ahead, args.frames)):
+        if rank == 0:
+            render(j)
+        stage(j)
     t_win, n_win, vox_win = 0.0, 0, 0
     for k in range(args.frames):
         has_next = k + 1 < args.frames
-        if has_next and rank == 0:
-            render(k + 1)  # (rendering is not timed)
+        has_ahead = k + ahead < args.frames
+        if has_ahead and rank == 0:
+            render(k + ahead)  # (not timed; buffer (k + ahead) % 3 was last used by frame k + ahead - 3, uploaded long ago)
         pose = capi.make_pose(synth.walk_pose(k, args.total))
         barrier()
         t0 = time.perf_counter()
-        if has_next:
-            stage(k + 1)
+        if has_ahead:
+            stage(k + ahead)
         rc = L.tf_integrate_frame(m.h, k, int(k % 10 == 0), C.byref(pose), C.byref(camc), C.byref(st), None, None, None, None, 0)
         assert rc == 0, L.tf_last_error(m.h)
         if has_next:
