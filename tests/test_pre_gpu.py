@@ -215,3 +215,32 @@ def test_raw_depth_conversion_and_bilateral_filter():
     G.m.upload_frame(3, flat)
     G.m.pre_bilateral(3)
     assert eq(G.m.pre_download(3, depth=True)["depth"], flat)
+
+
+def test_empty_frames_holes_and_identity_transform():
+    """Edge inputs: an all-zero frame, frames with large holes (depth 0 -> 0/0 projections), the identity
+    transform (a frame refined against itself), a camera with integer principal point."""
+    W, H = 640, 480
+    rng = np.random.default_rng(21)
+    camf = tuple(np.float32(x) for x in (525.0, 525.0, 320.0, 240.0))
+    O = live_oracle()
+    G = GpuPre(W, H)
+    base = (1.0 + 0.5 * rng.random((H, W))).astype(np.float32)
+    holes = base.copy()
+    holes[rng.random((H, W)) < 0.3] = 0.0
+    holes[100:200, 300:500] = 0.0
+    zero = np.zeros((H, W), np.float32)
+    I = np.eye(4)
+    T = np.eye(4)
+    T[:3, 3] = (0.01, -0.02, 0.015)
+    for kd, nd, X in ((holes, base, T), (base, holes, T), (zero, base, T), (base, zero, T), (holes, holes, I)):
+        assert eq(G.normal_map(kd, camf), O.normal_map(kd, camf))
+        w = np.zeros_like(kd)
+        d1, w1 = O.refine_keyframe(kd, w, nd, X, camf)
+        (g1, gw1), = G.refine_keyframe_n(kd, nd, X, camf, 1)
+        assert eq(g1, d1) and eq(gw1, w1)
+        n0, a, n1, b = G.new_frame_path(d1, nd, np.linalg.inv(X), camf)
+        on = O.normal_map(nd, camf)
+        oa = O.refine_newframe(d1, nd, np.linalg.inv(X), camf)
+        on1, ob = O.refine_depth_by_normal(on, oa, camf)
+        assert eq(n0, on) and eq(a, oa) and eq(n1, on1) and eq(b, ob)
