@@ -368,11 +368,11 @@ def main():
            "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / args.steps,
            "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / args.steps,
            "ms_per_step": 1e3 * e2e_s / args.steps, "median_ms_per_step": 1e3 * float(np.median(step_s)),
-           "mode": ("double buffered: tf_integrate_frame_begin(i) | tf_upload_frame(i+1) | tf_integrate_frame_end(i) | "
-                    "tf_wait_upload(i+1), host buffers page-locked" if dist is None else
-                    "double buffered: tf_integrate_frame_begin(i) on every rank's shard | rank 0 uploads frame i+1, "
-                    "tf_broadcast_frame (one ncclBroadcast inside the library, on the copy stream) | tf_integrate_frame_end(i) | "
-                    "tf_wait_upload(i+1); no Python between the C calls")}
+           "mode": ("one tf_stream_step call per step = tf_integrate_frame_begin(i) | tf_upload_frame(i+1) | "
+                    "tf_integrate_frame_end(i) | tf_wait_upload(i+1) inside the library, host buffers page-locked" if dist is None else
+                    "one tf_stream_step call per step and rank = tf_integrate_frame_begin(i) on the rank's shard | rank 0 uploads "
+                    "frame i+2, tf_broadcast_frame (one ncclBroadcast inside the library, on the copy stream) | "
+                    "tf_integrate_frame_end(i) | tf_wait_upload(i+1)")}
     # The map the e2e pass built (frames 0..warmup+steps-1 from empty), as a shard-independent checksum:
     # the same at every N and in the reference arm's line if and only if the fused maps are identical.
     from texturefusion_b200.maphash import map_hash

@@ -215,6 +215,28 @@ int tf_integrate_frame_begin(tf_map* m, int32_t frame_index, int use_color, cons
                              int64_t cap);
 int tf_integrate_frame_end(tf_map* m, tf_frame_stats* stats_out);
 
+/* One step of the streaming loop above as ONE call (what a caller in a language with an expensive foreign-call
+ * boundary wants): tf_integrate_frame_begin(frame) | tf_upload_frame(next) (when next_depth is given) |
+ * tf_broadcast_frame(next) (maps with a communicator, when next_index >= 0) | tf_integrate_frame_end | tf_wait_upload(wait_index)
+ * (when wait_index >= 0).  Same results and errors as the separate calls; the first error ends the step. */
+typedef struct {
+  int32_t frame_index, use_color;   /* the frame to fuse (its ingest was queued by an earlier step) */
+  tf_pose pose;
+  tf_chunk_id* ids_out;             /* as tf_integrate_frame */
+  uint8_t* is_new_out;
+  uint8_t* updated_out;
+  float* quality_out;
+  int64_t cap;
+  int32_t next_index;               /* frame to ingest while `frame_index` is being fused; < 0: none */
+  int32_t next_has_color;           /* (sharded maps) planes tf_broadcast_frame moves */
+  const float* next_depth;          /* host planes of that frame on the ingest rank, NULL on the others */
+  const uint8_t* next_rgba;
+  const float* next_quality;
+  int32_t broadcast_root;
+  int32_t wait_index;               /* frame whose ingest has completed when the call returns; < 0: none */
+} tf_stream_step_args;
+int tf_stream_step(tf_map* m, const tf_camera* cam, const tf_stream_step_args* step, tf_frame_stats* stats_out);
+
 /* Loop-closure path (GCFusion/MobileFusion.cpp:301-310): one item = one
  * ReIntegrateKeyframe call (:114-221).  flag 0: de-integrate the key-frame and its local
  * frames with their old poses over `ids` (= kf.validChunks).  flag 1: Prepare with the

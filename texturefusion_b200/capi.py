@@ -22,7 +22,7 @@ EXPORTS = [
     "tf_upload_frame", "tf_upload_keyframe_rgb", "tf_release_frame", "tf_frame_device_ptrs",
     "tf_comm_unique_id", "tf_comm_init", "tf_broadcast_frame",
     "tf_prepare", "tf_integrate", "tf_integrate_group", "tf_remove_chunks", "tf_integrate_frame", "tf_integrate_frame_begin", "tf_integrate_frame_end",
-    "tf_integrate_batch", "tf_mesh_chunks", "tf_has_chunk", "tf_chunk_count", "tf_list_chunks", "tf_download_chunks",
+    "tf_stream_step", "tf_integrate_batch", "tf_mesh_chunks", "tf_has_chunk", "tf_chunk_count", "tf_list_chunks", "tf_download_chunks",
     "tf_atlas_alloc_slot", "tf_atlas_update", "tf_atlas_download", "tf_atlas_patch_size", "tf_patch_texcoords", "tf_sync", "tf_wait_upload",
     "tf_pre_upload_depth_u16", "tf_pre_bilateral", "tf_pre_normal_map", "tf_pre_refine_keyframe", "tf_pre_refine_newframe", "tf_pre_refine_depth_by_normal", "tf_pre_color_quality",
     "tf_pre_download",
@@ -47,6 +47,14 @@ class Truncation(C.Structure):
 
 class Pose(C.Structure):
     _fields_ = [("m", C.c_float * 16)]
+
+
+class StreamStepArgs(C.Structure):
+    _fields_ = [("frame_index", C.c_int32), ("use_color", C.c_int32), ("pose", Pose),
+                ("ids_out", C.c_void_p), ("is_new_out", C.c_void_p), ("updated_out", C.c_void_p), ("quality_out", C.c_void_p),
+                ("cap", C.c_int64), ("next_index", C.c_int32), ("next_has_color", C.c_int32),
+                ("next_depth", C.c_void_p), ("next_rgba", C.c_void_p), ("next_quality", C.c_void_p),
+                ("broadcast_root", C.c_int32), ("wait_index", C.c_int32)]
 
 
 class Config(C.Structure):
@@ -123,6 +131,7 @@ def load() -> C.CDLL:
                                      C.POINTER(FrameStats), vp, vp, vp, vp, i64]
     L.tf_integrate_frame_begin.argtypes = [vp, C.c_int32, C.c_int, C.POINTER(Pose), C.POINTER(Camera), vp, vp, vp, vp, i64]
     L.tf_integrate_frame_end.argtypes = [vp, C.POINTER(FrameStats)]
+    L.tf_stream_step.argtypes = [vp, C.POINTER(Camera), C.POINTER(StreamStepArgs), C.POINTER(FrameStats)]
     L.tf_integrate_batch.argtypes = [vp, C.POINTER(BatchItem), i64, C.POINTER(Camera)]
     L.tf_has_chunk.argtypes = [vp, ChunkId]
     L.tf_chunk_count.argtypes = [vp]

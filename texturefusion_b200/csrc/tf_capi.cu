@@ -1322,6 +1322,23 @@ int tf_integrate_frame_end(tf_map* m, tf_frame_stats* stats_out) {
   return fused_group_end(m, stats_out);
 }
 
+int tf_stream_step(tf_map* m, const tf_camera* cam, const tf_stream_step_args* a, tf_frame_stats* stats_out) {
+  if (!m || !a) return fail(m, TF_ERR_INVALID, "tf_stream_step: bad argument");
+  if (int rc = tf_integrate_frame_begin(m, a->frame_index, a->use_color, &a->pose, cam, a->ids_out, a->is_new_out, a->updated_out,
+                                        a->quality_out, a->cap))
+    return rc;
+  int rc_in = TF_OK;  // (the fused frame is in flight: it is collected below whatever the ingest calls return)
+  if (a->next_index >= 0) {
+    if (a->next_depth) rc_in = tf_upload_frame(m, a->next_index, a->next_depth, a->next_rgba, a->next_quality);
+    if (!rc_in && m->comm) rc_in = tf_broadcast_frame(m, a->next_index, a->next_has_color, a->broadcast_root);
+  }
+  const std::string err_in = rc_in ? m->err : std::string();
+  if (int rc = tf_integrate_frame_end(m, stats_out)) return rc;
+  if (rc_in) return fail(m, rc_in, err_in);
+  if (a->wait_index >= 0) return tf_wait_upload(m, a->wait_index);
+  return TF_OK;
+}
+
 // ---- loop-closure batches ---------------------------------------------------------------------------
 //
 // All items of a batch are queued without intermediate host synchronisation: de-integration =

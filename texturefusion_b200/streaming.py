@@ -10,7 +10,9 @@ N GPUs:       every rank queues frame i on its shard (tf_integrate_frame_begin);
               SM slot, and integrate_kernel occupies every SM while it runs, so a broadcast queued one
               frame ahead would only start when the frame's kernels end and then sit on the critical path
               of the next frame; queued two ahead it runs in the bbox / culling phase of the frame between.
-All arguments are marshalled once; a step is four or five C calls and no Python glue in between.
+All arguments are marshalled once.  `step` is ONE C call (tf_stream_step = the sequence above inside the library:
+a foreign call from Python costs 1-3 us, four or five of them would be a tenth of a step); the separate
+calls stay available (`fuse_begin` / `stage` / `fuse_end` / `wait`, `step_calls`) and give the same results.
 """
 from __future__ import annotations
 
@@ -46,6 +48,29 @@ class FrameStreamer:
         self.out_new = capi.PinnedBuffer((cap,), np.uint8)
         self.out_upd = capi.PinnedBuffer((cap,), np.uint8)
         self.out_q = capi.PinnedBuffer((cap,), np.float32)
+
+        self._steps = {}
+
+    def _step_args(self, i):
+        """tf_stream_step arguments of step(i), built once per frame of the ring."""
+        a = self._steps.get(i)
+        if a is None:
+            fr, nx = self.frames[i], (i + self.lookahead) % self.nf
+            fn = self.frames[nx]
+            a = capi.StreamStepArgs()
+            a.frame_index, a.use_color, a.pose = fr.index, int(fr.is_keyframe), self.poses[i]
+            if self.want_lists:
+                a.ids_out, a.is_new_out, a.updated_out, a.quality_out = self.out_ids.ptr, self.out_new.ptr, self.out_upd.ptr, self.out_q.ptr
+                a.cap = self.cap
+            a.next_index, a.next_has_color = fn.index, int(fn.is_keyframe)
+            if self.rank == 0:
+                a.next_depth = self.pin_d[nx].ptr
+                if fn.is_keyframe:
+                    a.next_rgba, a.next_quality = self.pin_c[nx].ptr, self.pin_q[nx].ptr
+            a.broadcast_root = 0
+            a.wait_index = self.frames[(i + 1) % self.nf].index
+            self._steps[i] = a
+        return a
 
     def _ok(self, rc):
         if rc != 0:
@@ -97,6 +122,11 @@ class FrameStreamer:
     def step(self, i):
         """One end-to-end step for frame i (frames i .. i+lookahead-1 have been staged): one frame's ingest
         is queued while this frame's kernels run, and the NEXT frame to be fused has arrived when the step ends."""
+        self._ok(self.L.tf_stream_step(self.m.h, C.byref(self.camc), C.byref(self._step_args(i)), C.byref(self.st)))
+        return self.st.n_chunks
+
+    def step_calls(self, i):
+        """The same step as separate C calls."""
         self.fuse_begin(i)                           # frame i's kernels are running ...
         self.stage((i + self.lookahead) % self.nf)   # ... while the host queues a later frame's copy (+ broadcast)
         n = self.fuse_end()
