@@ -25,7 +25,7 @@ struct PreXf {  // rigid transform, rows of [R | t]
   float r[3][3], t[3];
 };
 
-// RSQRTPS for the operands these loops produce (see oracle/tf_pre_oracle.cpp for the special cases)
+// RSQRTPS: the table for positive normal operands; zero / denormal -> inf, negative -> NaN, inf -> 0 as the instruction does
 __device__ __forceinline__ float rsqrt_x86(float x) {
   const unsigned b = __float_as_uint(x), e = (b >> 23) & 0xffu, m = b & 0x7fffffu;
   unsigned r;
