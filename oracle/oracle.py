@@ -166,7 +166,28 @@ def truncation_distance(z: float, trunc=DEFAULT_TRUNC, impl: str = "port") -> fl
     return float(L.tfo_truncation_distance(t, C.c_float(z)))
 
 
-def patch_texcoords(rgb, depth, world_to_camera, cam, offsets, vertices, colors):
+_PATCH_REF = None
+
+
+def have_patch_ref() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libtexfusion_ref_patch.so"))
+
+
+def _patch_lib(impl: str):
+    """impl "port": the restatement in tf_oracle.cpp; "ref": the reference's own Structure/Patch.cpp functions
+    (oracle/ref_patch_driver.cpp)."""
+    global _PATCH_REF
+    if impl == "port":
+        return _lib()
+    if _PATCH_REF is None:
+        L = C.CDLL(os.path.join(_HERE, "_ref", "libtexfusion_ref_patch.so"))
+        vp = C.c_void_p
+        L.tfo_patch_texcoords.argtypes = [vp, vp, vp, C.POINTER(_Cam), C.c_int64, vp, vp, vp, vp, vp, vp]
+        _PATCH_REF = L
+    return _PATCH_REF
+
+
+def patch_texcoords(rgb, depth, world_to_camera, cam, offsets, vertices, colors, impl: str = "port"):
     """Patch::CalculateTexCoords (Structure/Patch.cpp:40-108) for a batch of meshes on the CPU."""
     rgb = np.ascontiguousarray(rgb, np.uint8)
     d = np.ascontiguousarray(depth, np.float32)
@@ -177,8 +198,8 @@ def patch_texcoords(rgb, depth, world_to_camera, cam, offsets, vertices, colors)
     tc = np.empty((len(v), 2), np.float32)
     col = np.empty((len(v), 3), np.float32)
     res = np.empty((max(n, 1), 6), np.int32)
-    _lib().tfo_patch_texcoords(_p(rgb), _p(d), _p(_pose(world_to_camera)), C.byref(_cam(cam)), n, _p(off), _p(v), _p(c),
-                               _p(tc), _p(col), _p(res))
+    _patch_lib(impl).tfo_patch_texcoords(_p(rgb), _p(d), _p(_pose(world_to_camera)), C.byref(_cam(cam)), n, _p(off), _p(v), _p(c),
+                                         _p(tc), _p(col), _p(res))
     return tc, col, res[:n]
 
 

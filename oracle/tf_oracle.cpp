@@ -16,6 +16,8 @@
 // choose: the association order of Eigen's 3-term products (runtime switch below;
 // tools/ref_golden/ is the recipe for a machine that has Eigen).  Also checked against an
 // independent scalar restatement (oracle/scalar_ref.py) and hand-computed known-answer cases.
+// tfo_patch_texcoords is pinned by oracle/_ref/libtexfusion_ref_patch.so (the reference's own
+// Patch::CalculateTexCoords / bilinear / bilinear_depth, oracle/ref_patch_driver.cpp; tests/test_patch.py).
 //
 // Arithmetic rules it follows (see DESIGN.md "Arithmetic contract"):
 //   * the reference is built with -mavx2 and WITHOUT -mfma (CMakeLists.txt:57-58): every

@@ -94,3 +94,21 @@ def test_gpu_patch_texcoords_bit_exact():
     g.atlas_update(patches)
     with pytest.raises(capi.TexFusionError):
         g.patch_texcoords(12345, T, cam, offs, v, c)
+
+
+def test_restatement_equals_reference_patch_sources():
+    """Structure/Patch.cpp's own CalculateTexCoords / bilinear / bilinear_depth (oracle/_ref/libtexfusion_ref_patch.so)
+    against the restatement the GPU kernel is checked with: texcoords, texcolours, boxes, votes, flags, bit for bit."""
+    from oracle import have_patch_ref
+    if not have_patch_ref():
+        pytest.skip("oracle/_ref/libtexfusion_ref_patch.so not built")
+    cam, kf = keyframe()
+    T = world_to_camera(kf.pose)
+    for seed in (3, 4):
+        off, v, c = pseudo_meshes(cam, kf, n_patches=300, seed=seed)
+        a = oracle_patch(kf.rgb, kf.depth, T, cam, off, v, c, impl="port")
+        b = oracle_patch(kf.rgb, kf.depth, T, cam, off, v, c, impl="ref")
+        assert np.array_equal(a[2], b[2])
+        assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32))
+        assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+        assert (a[2][:, 4] == 1).sum() > 0 and (a[2][:, 5] == -1).sum() > 0  # wrong_mapping and off-image cases occur
