@@ -5,6 +5,9 @@
                    oracle/eigen_standin (ref_driver.cpp); built here, where /root/reference exists,
                    and shipped prebuilt to the GPU box
   impl="ref_l2r"   the same with left-to-right 3-term products (Eigen 3.2 association)
+  impl="ref_chisel" the same driver around the reference's own chisel::Chisel object (Structure/Chisel.h inline
+                   methods instead of the restated glue; ref_driver.cpp -DTF_REF_REAL_CHISEL) — for lists below the
+                   reference's threading threshold of 1000 chunks
 """
 from __future__ import annotations
 
@@ -48,7 +51,8 @@ def ref_lib_path(impl: str = "ref") -> str:
     ov = os.environ.get("TF_REF_LIB")
     if ov and (impl == "ref_l2r") == (os.environ.get("TF_REF_ORDER") == "l2r"):
         return ov
-    return os.path.join(_HERE, "_ref", "libtexfusion_ref.so" if impl == "ref" else "libtexfusion_ref_l2r.so")
+    return os.path.join(_HERE, "_ref", {"ref": "libtexfusion_ref.so", "ref_l2r": "libtexfusion_ref_l2r.so",
+                                        "ref_chisel": "libtexfusion_ref_chisel.so"}[impl])
 
 
 def have_ref(impl: str = "ref") -> bool:

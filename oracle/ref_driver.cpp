@@ -12,9 +12,17 @@
 // against oracle/eigen_standin (Eigen itself is absent from this image; the stand-in's header states
 // what it restates and the one freedom it has: the association order of 3-term products).
 //
-// Structure/Chisel.{h,cpp} cannot be compiled (OpenCV, Sophus via GCSLAM/frame.h); the few lines of
-// glue it adds on this path are restated below, each citing the lines it follows.  Everything
+// Structure/Chisel.{h,cpp} need OpenCV and Sophus (via Atlas.h, Patch.h, GCSLAM/frame.h); the few lines of
+// glue Chisel.h adds on this path are restated below, each citing the lines it follows.  Everything
 // voxel- or pixel-sized runs in the reference's code.
+//
+// -DTF_REF_REAL_CHISEL (oracle/_ref/libtexfusion_ref_chisel.so) builds the same driver around the reference's OWN
+// chisel::Chisel: Structure/Chisel.h compiled with the stand-in <opencv2/opencv.hpp> / GCSLAM/frame.h of
+// oracle/cv_standin, its out-of-line constructor / Reset / bufferIntegratorSIMDCentroids and Atlas's constructor cut
+// out of Chisel.cpp / Atlas.cpp (oracle/ref_pre_slices.py chisel).  prepare / integrate / finalize then ARE
+// Chisel::PrepareIntersectChunks, IntegrateDepthScanColor (list form) and FinalizeIntegrateChunks; tests/test_ref_cpu.py
+// requires that build and the restated glue to agree (on lists short enough for the reference's parallel_for to stay
+// on one thread: its concurrent std::vector<bool> writes are a race a checker must not run).
 //
 // The exported tfo_* symbols have the signatures of oracle/tf_oracle.cpp, so oracle.py drives
 // either library.  NOTE ChunkManager::GetIDAt caches 1/(8*res) in function-local statics
@@ -26,6 +34,12 @@
 #include <thread>
 #include <vector>
 
+#ifdef TF_REF_REAL_CHISEL
+#include "Chisel.h"
+namespace chisel {
+#include TF_REF_CHISEL_SLICES
+}  // namespace chisel
+#endif
 #include "ChunkManager.h"
 #include "camera/PinholeCamera.h"
 #include "geometry/Chunk.h"
@@ -47,13 +61,23 @@ struct Cam {  // == tf_camera
 
 struct RefMap {
   EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+#ifdef TF_REF_REAL_CHISEL
+  Chisel chisel;                 // the reference's own object; the two references below are its public fields
+  ChunkManager& chunkManager;    // (Structure/Chisel.h:488-489)
+  ChunkSet& meshesToUpdate;
+#else
   ChunkManager chunkManager;
-  ProjectionIntegrator integrator;
   ChunkSet meshesToUpdate;
+#endif
+  ProjectionIntegrator integrator;
   float res;
   int threads;  // 1: serial loop; 0: the reference's parallel_for policy
   RefMap(float r, const float* t5, int th)
+#ifdef TF_REF_REAL_CHISEL
+      : chisel(Eigen::Vector3i(8, 8, 8), r, true), chunkManager(chisel.chunkManager), meshesToUpdate(chisel.meshesToUpdate), res(r), threads(th) {
+#else
       : chunkManager(Eigen::Vector3i(8, 8, 8), r, true), res(r), threads(th) {
+#endif
     // MobileFusion::initChiselMap (GCFusion/MobileFusion.h:243-251)
     integrator.SetCentroids(chunkManager.GetCentroids());
     integrator.SetTruncator(TruncatorPtr(new QuadraticTruncator(t5[0], t5[1], t5[2], t5[3])));
@@ -86,6 +110,10 @@ Transform make_pose(const float* m16) {  // column-major 4x4, camera -> world
 // needs OpenCV.  The expression of :67-69 is kept verbatim so that it evaluates through the same
 // (stand-in) Eigen operators.
 void buffer_centroids(RefMap* m, const Transform& depthExtrinsic) {
+#ifdef TF_REF_REAL_CHISEL
+  m->chisel.bufferIntegratorSIMDCentroids(m->integrator, depthExtrinsic);
+  return;
+#endif
   ChunkManager& chunkManager = m->chunkManager;
   ProjectionIntegrator& integrator = m->integrator;
   Vec3 halfVoxel = Vec3(chunkManager.GetResolution(), chunkManager.GetResolution(), chunkManager.GetResolution()) * 0.5f;
@@ -115,6 +143,11 @@ void buffer_centroids(RefMap* m, const Transform& depthExtrinsic) {
 // Chisel::PrepareIntersectChunks (Structure/Chisel.h:103-140)
 void prepare(RefMap* m, float* depthImage, const Transform& depthExtrinsic, const PinholeCamera& depthCamera,
              ChunkIDList& chunksIntersecting, std::vector<bool>& needsUpdateFlag, std::vector<bool>& newChunkFlag) {
+#ifdef TF_REF_REAL_CHISEL
+  m->chisel.PrepareIntersectChunks(m->integrator, depthImage, depthExtrinsic, depthCamera, chunksIntersecting, needsUpdateFlag,
+                                   newChunkFlag);
+  return;
+#endif
   buffer_centroids(m, depthExtrinsic);
   chunksIntersecting.clear();
   needsUpdateFlag.clear();
@@ -142,6 +175,16 @@ void prepare(RefMap* m, float* depthImage, const Transform& depthExtrinsic, cons
 void integrate(RefMap* m, float* depthImage, unsigned char* colorImage, const Transform& depthExtrinsic,
                const PinholeCamera& depthCamera, ChunkIDList& chunksIntersecting, std::vector<uint8_t>& needsUpdateFlag,
                int integrate_flag, int keyframeID, float* observationQualityPointer, float* q_out) {
+#ifdef TF_REF_REAL_CHISEL
+  {  // (q_out, the raw per-chunk quality sum, does not leave the reference's function: reported as 0)
+    std::vector<bool> nu(needsUpdateFlag.begin(), needsUpdateFlag.end());
+    m->chisel.IntegrateDepthScanColor(m->integrator, depthImage, colorImage, depthExtrinsic, depthCamera, chunksIntersecting, nu,
+                                      integrate_flag, keyframeID, observationQualityPointer);
+    for (size_t i = 0; i < nu.size(); i++) needsUpdateFlag[i] = nu[i] ? 1 : 0;
+    if (q_out) std::fill(q_out, q_out + chunksIntersecting.size(), 0.0f);
+    return;
+  }
+#endif
   buffer_centroids(m, depthExtrinsic);
   if (chunksIntersecting.size() < 1) return;
   std::vector<int> threadIndex;
@@ -163,6 +206,13 @@ void integrate(RefMap* m, float* depthImage, unsigned char* colorImage, const Tr
 // Chisel::FinalizeIntegrateChunks + GarbageCollect (Structure/Chisel.h:184-216, 472-477)
 void finalize(RefMap* m, ChunkIDList& chunksIntersecting, std::vector<uint8_t>& needsUpdateFlag,
               std::vector<bool>& newChunkFlag, ChunkIDList& validChunks) {
+#ifdef TF_REF_REAL_CHISEL
+  {
+    std::vector<bool> nu(needsUpdateFlag.begin(), needsUpdateFlag.end());
+    m->chisel.FinalizeIntegrateChunks(chunksIntersecting, nu, newChunkFlag, validChunks);
+    return;
+  }
+#endif
   validChunks.clear();
   ChunkIDList garbageChunks;
   for (int i = 0; i < (int)chunksIntersecting.size(); i++) {
@@ -200,7 +250,9 @@ extern "C" {
 struct tfo_map;
 
 const char* tfo_impl() {
-#ifdef EIGEN_STANDIN_LEFT_TO_RIGHT
+#ifdef TF_REF_REAL_CHISEL
+  return "reference sources incl. chisel::Chisel (Chisel.h + Chisel.cpp / Atlas.cpp slices) + Eigen / cv stand-ins";
+#elif defined(EIGEN_STANDIN_LEFT_TO_RIGHT)
   return "reference sources + Eigen stand-in (left-to-right products)";
 #else
   return "reference sources + Eigen stand-in (tree-reduced products)";
@@ -216,6 +268,10 @@ int tfo_threads_used(tfo_map* h) {
 }
 void tfo_reset(tfo_map* h) {  // Chisel::Reset (Structure/Chisel.cpp:47-50)
   RefMap* m = (RefMap*)h;
+#ifdef TF_REF_REAL_CHISEL
+  m->chisel.Reset();
+  return;
+#endif
   m->chunkManager.Reset();
   m->meshesToUpdate.clear();
 }
