@@ -390,9 +390,15 @@ int tf_get_kernel_time(tf_map* m, int reset, double* integrate_ms, int64_t* inte
                        double* integrate_bytes);
 
 /* Test hook: runs both pixel-projection paths of integrate_kernel (tf_device.cuh:
- * project_fast / project_exact) on n caller-provided (c, cz) pairs. */
+ * project_safe / project_exact) on n caller-provided (c, cz) pairs; accepted[i] != 0 where the pair
+ * lies in the operand range the kernel's per-chunk test guarantees for project_safe. */
 int tf_debug_project(tf_map* m, const float* c, const float* cz, int64_t n, float f, float ch,
                      int32_t* u_fast, int32_t* u_exact, uint8_t* accepted);
+/* Test hook: the running average's quotient as integrate_kernel forms it (div.rn's fast-path
+ * sequence inline, IEEE division out of line where its result is not kept) and __fdiv_rn, on n
+ * caller-provided (numerator, divisor) pairs; accepted[i] != 0 where the inline result was kept. */
+int tf_debug_divide(tf_map* m, const float* num, const float* den, int64_t n, float* q_kernel,
+                    float* q_ieee, uint8_t* accepted);
 
 #ifdef __cplusplus
 }

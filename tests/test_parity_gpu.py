@@ -196,10 +196,12 @@ def test_errors_and_edge_cases():
 
 
 def test_fast_projection_never_disagrees_with_exact_path():
-    """integrate_kernel rounds pixel coordinates with a division-free fast path that must either
-    agree with the reference's three-op expression or decline (tf_device.cuh: project_fast).
-    Random operands over the working range plus operands engineered to land next to the
-    rounding boundaries k + 0.5, zeros, negatives, tiny/huge depths, NaN and inf."""
+    """integrate_kernel evaluates the reference's (c/cz)*f + ch division-free (tf_device.cuh: project_safe
+    = div.rn's own fast-path sequence without its range check) for chunks whose voxel centres pass a range
+    test; inside that range it must equal the three IEEE ops bit for bit.  Random operands over the
+    working range, operands engineered to land next to the rounding boundaries k + 0.5, quotients next
+    to representable values' midpoints, the edges of the accepted range, tiny numerators; outside the
+    range (zeros, denormals, huge, inf, NaN) the hook only has to report `not accepted`."""
     g = capi.Map(0.02)
     rng = np.random.RandomState(5)
     n = 1 << 22
@@ -210,17 +212,58 @@ def test_fast_projection_never_disagrees_with_exact_path():
     k = rng.randint(-50, 700, n // 2)
     target = (k + 0.5 + rng.uniform(-2e-3, 2e-3, n // 2)).astype(np.float64)
     c[: n // 2] = ((target - float(ch)) / float(f) * cz[: n // 2].astype(np.float64)).astype(np.float32)
-    special = np.array([0.0, -0.0, 1e-30, -1e-30, 1e-40, 1e30, -1e30, np.inf, -np.inf, np.nan, 3e38, 1.0], np.float32)
+    # the whole accepted range, log-uniform, both signs of the numerator
+    m = 1 << 21
+    cz_w = np.exp2(rng.uniform(-17, 21, m)).astype(np.float32)
+    c_w = (np.exp2(rng.uniform(-140, 21, m)) * rng.choice([-1.0, 1.0], m)).astype(np.float32)
+    # divisors with all-ones / all-zeros mantissas and their neighbours (the hard cases of the Newton step)
+    e = rng.randint(-16, 20, m).astype(np.float64)
+    mant = rng.choice([1.0, 1.0 + 2.0 ** -23, 2.0 - 2.0 ** -23, 2.0 - 2.0 ** -22, 1.5, 1.0 + 2.0 ** -22], m)
+    cz_m = (mant * np.exp2(e)).astype(np.float32)
+    c_m = (rng.uniform(-2.0, 2.0, m) * cz_m).astype(np.float32)
+    special = np.array([0.0, -0.0, 1e-30, -1e-30, 1e-40, 1e30, -1e30, np.inf, -np.inf, np.nan, 3e38, 1.0,
+                        2.0 ** -17, 2.0 ** 21, 2.0 ** -103, 2.0 ** -126, 1e-45], np.float32)
     cs, zs = np.meshgrid(special, special)
-    c = np.concatenate([c, cs.ravel()])
-    cz = np.concatenate([cz, zs.ravel()])
+    c = np.concatenate([c, c_w, c_m, cs.ravel()])
+    cz = np.concatenate([cz, cz_w, cz_m, zs.ravel()])
     tot_acc = 0
-    for (ff, cc) in ((f, ch), (np.float32(525.0), np.float32(239.5)), (np.float32(131.0), np.float32(79.5))):
+    for (ff, cc) in ((f, ch), (np.float32(525.0), np.float32(239.5)), (np.float32(131.0), np.float32(79.5)),
+                     (np.float32(2100.0), np.float32(1023.5)), (np.float32(1.0), np.float32(0.5))):
         uf, ue, acc = g.debug_project(c, cz, ff, cc)
-        bad = (acc != 0) & (uf != ue)
-        assert not bad.any(), f"{bad.sum()} accepted fast-path results differ, e.g. c={c[bad][:3]} cz={cz[bad][:3]}"
+        ue_sat = ue.copy()
+        # cvtps_epi32 returns 0x80000000 where __float2int_rn saturates: both are "off the image" for the kernel
+        off = (ue == np.int32(-2 ** 31)) & ((uf == np.int32(2 ** 31 - 1)) | (uf == np.int32(-2 ** 31)))
+        bad = (acc != 0) & (uf != ue_sat) & ~off
+        assert not bad.any(), f"{bad.sum()} in-range results differ, e.g. c={c[bad][:3]} cz={cz[bad][:3]} {uf[bad][:3]} {ue[bad][:3]}"
         tot_acc += acc[: n].mean()
-    assert tot_acc / 3 > 0.5  # the fast path is actually taken (engineered half declines by design)
+    assert tot_acc / 5 == 1.0  # the working range is inside the accepted range
+
+
+def test_inline_division_of_the_running_average_is_the_ieee_quotient():
+    """Phase B of integrate_kernel forms (s w + sd w') / (w + w' + 1e-4) with div.rn's fast-path sequence
+    inline and redoes it with the IEEE division when the result is not a number of at least 2^-60 in
+    magnitude.  Whatever the operands, the value it keeps must be the IEEE quotient (bit for bit,
+    signed zeros included) for every divisor the kernel can pass (> 0.5)."""
+    g = capi.Map(0.02)
+    rng = np.random.RandomState(11)
+    n = 1 << 22
+    den = np.concatenate([rng.uniform(0.5001, 400.0, n // 2), np.exp2(rng.uniform(-1, 127.9, n // 2))]).astype(np.float32)
+    num = np.concatenate([rng.uniform(-0.2, 0.2, n // 4) * den[: n // 4], np.exp2(rng.uniform(-149, 127, n - n // 4)) *
+                          rng.choice([-1.0, 1.0], n - n // 4)]).astype(np.float32)
+    e = rng.randint(0, 30, n).astype(np.float64)
+    mant = rng.choice([1.0, 1.0 + 2.0 ** -23, 2.0 - 2.0 ** -23, 2.0 - 2.0 ** -22, 1.5, 1.0 + 2.0 ** -22], n)
+    den_m = (mant * np.exp2(e)).astype(np.float32)
+    num_m = (rng.uniform(-3.0, 3.0, n) * den_m).astype(np.float32)
+    special_n = np.array([0.0, -0.0, 1e-45, -1e-45, 1e-38, 2.0 ** -103, -2.0 ** -104, 2.0 ** -61, 2.0 ** -60, 1e-30, 1e30, -1e30,
+                          3e38, np.inf, -np.inf, np.nan, 999.0, 1.0], np.float32)
+    special_d = np.array([0.50001, 0.5001, 1.0, 1.0001, 3.0, 2.0 ** 60, 2.0 ** 125, 2.0 ** 126, 2.0 ** 127, 3e38, np.inf], np.float32)
+    ns, ds = np.meshgrid(special_n, special_d)
+    num = np.concatenate([num, num_m, ns.ravel()])
+    den = np.concatenate([den, den_m, ds.ravel()])
+    qk, qi, acc = g.debug_divide(num, den)
+    same = (qk.view(np.uint32) == qi.view(np.uint32)) | (np.isnan(qk) & np.isnan(qi))
+    assert same.all(), f"{(~same).sum()} quotients differ, e.g. num={num[~same][:4]} den={den[~same][:4]} {qk[~same][:4]} {qi[~same][:4]}"
+    assert acc[: n // 4].mean() > 0.99  # the inline result is the one normally kept
 
 
 def _oracle_keyframe_group(o, cam, group, poses, flag, ids=None):

@@ -26,7 +26,7 @@ EXPORTS = [
     "tf_atlas_alloc_slot", "tf_atlas_update", "tf_atlas_download", "tf_atlas_patch_size", "tf_patch_texcoords", "tf_sync", "tf_wait_upload",
     "tf_pre_upload_depth_u16", "tf_pre_bilateral", "tf_pre_normal_map", "tf_pre_refine_keyframe", "tf_pre_refine_newframe", "tf_pre_refine_depth_by_normal", "tf_pre_color_quality",
     "tf_pre_download",
-    "tf_get_counters", "tf_stream", "tf_copy_stream", "tf_set_profiling", "tf_get_kernel_time", "tf_get_stage_times", "tf_debug_project",
+    "tf_get_counters", "tf_stream", "tf_copy_stream", "tf_set_profiling", "tf_get_kernel_time", "tf_get_stage_times", "tf_debug_project", "tf_debug_divide",
 ]
 
 
@@ -164,6 +164,7 @@ def load() -> C.CDLL:
     L.tf_get_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]
     L.tf_get_stage_times.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.tf_debug_project.argtypes = [vp, vp, vp, i64, C.c_float, C.c_float, vp, vp, vp]
+    L.tf_debug_divide.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     _LIB = L
     return L
 
@@ -559,6 +560,14 @@ class Map:
         uf, ue, acc = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.uint8)
         self._check(self.L.tf_debug_project(self.h, _p(c), _p(cz), n, C.c_float(f), C.c_float(ch), _p(uf), _p(ue), _p(acc)))
         return uf, ue, acc
+
+    def debug_divide(self, num, den):
+        num = np.ascontiguousarray(num, np.float32)
+        den = np.ascontiguousarray(den, np.float32)
+        n = num.size
+        qk, qi, acc = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.uint8)
+        self._check(self.L.tf_debug_divide(self.h, _p(num), _p(den), n, _p(qk), _p(qi), _p(acc)))
+        return qk, qi, acc
 
     def stage_times(self, reset=True) -> dict:
         arr = (C.c_double * 6)()

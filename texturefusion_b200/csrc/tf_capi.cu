@@ -500,7 +500,7 @@ int build_group(tf_map* m, const tf_group_frame* frames, int n_frames, const tf_
     const bool color = frames[f].use_color != 0;
     if (color && !m->cfg.use_color) return fail(m, TF_ERR_INVALID, "map created with use_color = 0");
     if (color && !fsl.has_rgba) return fail(m, TF_ERR_NOT_FOUND, "frame has no colour plane");
-    make_frame_dev(frames[f].pose, *cam, frames[f].flag, fsl.depth, color ? fsl.rgba : nullptr,
+    make_frame_dev(frames[f].pose, *cam, m->cfg.voxel_res, frames[f].flag, fsl.depth, color ? fsl.rgba : nullptr,
                    (color && fsl.has_quality) ? fsl.quality : nullptr, gp.f[f]);
     color_flags[f] = color;
   }
@@ -645,7 +645,7 @@ int tf_create(tf_map** out, const tf_config* cfg) {
     delete m;
     return TF_ERR_INVALID;
   }
-  if (m->W > 2048 || m->H > 2048) {  // bound used by project_fast's error analysis (tf_device.cuh)
+  if (m->W > 2048 || m->H > 2048) {  // (16-bit crop coordinates of the atlas descriptors, 32-bit pixel indices)
     g_create_error = "frame larger than 2048x2048";
     delete m;
     return TF_ERR_INVALID;
@@ -2052,6 +2052,33 @@ int tf_debug_project(tf_map* m, const float* c, const float* cz, int64_t n, floa
     ok(cudaStreamSynchronize(m->stream));
   }
   cudaFree(dc); cudaFree(dz); cudaFree(duf); cudaFree(due); cudaFree(da);
+  return rc;
+}
+
+int tf_debug_divide(tf_map* m, const float* num, const float* den, int64_t n, float* q_kernel, float* q_ieee,
+                    uint8_t* accepted) {
+  if (!m || !num || !den || !q_kernel || !q_ieee || !accepted || n <= 0 || n > (1 << 26))
+    return fail(m, TF_ERR_INVALID, "tf_debug_divide: bad argument");
+  use_device(m);
+  float *dn = nullptr, *dd = nullptr, *dk = nullptr, *di = nullptr;
+  unsigned char* da = nullptr;
+  int rc = TF_OK;
+  auto ok = [&](cudaError_t e) {
+    if (e != cudaSuccess && rc == TF_OK) rc = fail(m, TF_ERR_CUDA, cudaGetErrorString(e));
+    return e == cudaSuccess;
+  };
+  if (ok(dmalloc(&dn, (size_t)n)) && ok(dmalloc(&dd, (size_t)n)) && ok(dmalloc(&dk, (size_t)n)) &&
+      ok(dmalloc(&di, (size_t)n)) && ok(dmalloc(&da, (size_t)n)) &&
+      ok(cudaMemcpyAsync(dn, num, n * 4, cudaMemcpyHostToDevice, m->stream)) &&
+      ok(cudaMemcpyAsync(dd, den, n * 4, cudaMemcpyHostToDevice, m->stream))) {
+    debug_divide_kernel<<<m->grid, kThreads, 0, m->stream>>>(dn, dd, (int)n, dk, di, da);
+    ok(cudaGetLastError());
+    ok(cudaMemcpyAsync(q_kernel, dk, n * 4, cudaMemcpyDeviceToHost, m->stream));
+    ok(cudaMemcpyAsync(q_ieee, di, n * 4, cudaMemcpyDeviceToHost, m->stream));
+    ok(cudaMemcpyAsync(accepted, da, n, cudaMemcpyDeviceToHost, m->stream));
+    ok(cudaStreamSynchronize(m->stream));
+  }
+  cudaFree(dn); cudaFree(dd); cudaFree(dk); cudaFree(di); cudaFree(da);
   return rc;
 }
 

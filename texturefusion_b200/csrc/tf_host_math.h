@@ -70,7 +70,7 @@ inline void make_cull_params(float res, const tf_truncation& tr, int l2r, const 
 }
 
 // voxelUpdateSIMD set-up (ProjectionIntegrator.cpp:74-130).
-inline void make_frame_dev(const tf_pose& pose, const tf_camera& cam, int flag, const float* depth,
+inline void make_frame_dev(const tf_pose& pose, const tf_camera& cam, float res, int flag, const float* depth,
                            const uchar4* rgba, const float* quality, FrameDev& f) {
   float R[9];
   pose_split(pose, R, f.Rt, f.t);
@@ -78,7 +78,18 @@ inline void make_frame_dev(const tf_pose& pose, const tf_camera& cam, int flag, 
   f.fx = (float)(int)cam.fx, f.fy = (float)(int)cam.fy;
   f.cxh = (float)((double)cx + 0.5);  // double add, rounded to float by _mm256_set1_ps
   f.cyh = (float)((double)cy + 0.5);
-  f.eps_u = proj_eps_abs(f.cxh), f.eps_v = proj_eps_abs(f.cyh);
+  // Range test of project_safe (tf_device.cuh): a voxel centre is origin + (Rt (x,y,z)) res + res/2 with
+  // x,y,z in 0..7, so |centre_k - origin_k| <= (7 (|Rt_k0| + |Rt_k1| + |Rt_k2|) + 0.5) res =: b_k (taken 1 % up
+  // for the roundings).  Chunks whose origin depth exceeds z_safe = b_2 + 2^-16 have every cz > 2^-17; the
+  // test is switched off (z_safe = inf) when a b_k is not small against 2^20 or the intrinsics are out of range.
+  double b[3];
+  bool sane = std::fabs((double)f.fx) < 1048576.0 && std::fabs((double)f.fy) < 1048576.0;
+  for (int k = 0; k < 3; k++) {
+    b[k] = 1.01 * (7.0 * (std::fabs((double)f.Rt[3 * k]) + std::fabs((double)f.Rt[3 * k + 1]) + std::fabs((double)f.Rt[3 * k + 2])) + 0.5) * (double)res;
+    sane = sane && b[k] < 1048576.0;  // (false for NaN)
+  }
+  f.z_safe = sane ? (float)(b[2] + 1.0 / 65536.0) * 1.0001f : INFINITY;
+  f.pad0 = 0.0f;
   f.W = cam.width, f.H = cam.height;
   f.near_p = cam.near_plane, f.far_p = cam.far_plane;
   f.flag = flag;
