@@ -115,7 +115,8 @@ def main():
         print(f"  {nm:18s} " + " ".join(f"{tr[b, k]:6.1f}" for b in range(0, 16)))
     tr = np.nanmean(np.stack(traces), axis=0)
     names_t = ["kernel n known", "loop top", "bulk issued", "p0 projected", "p0 gathered", "p0 chunk arrived", "p0 updated",
-               "p1 projected", "p1 gathered", "p1 (arrived)", "p1 updated", "frames done", "written back"]
+               "p1 projected", "p1 gathered", "p1 (arrived)", "p1 updated", "frames done", "written back", "ord shuffled",
+               "finalized", "while top"]
     print("per-warp trace (warp 0 of blocks 0,37,...; us after bbox start; mean over frames); chunk 0 | chunk 1")
     for k, nm in enumerate(names_t):
         a = " ".join(f"{tr[b, k]:6.1f}" for b in range(0, 16, 3))
