@@ -745,6 +745,62 @@ def test_near_and_far_planes_inside_the_depth_range(res):
     g.close()
 
 
+@pytest.mark.parametrize("res", (0.02, 0.005))
+def test_chunks_at_and_behind_the_camera_plane(res):
+    """integrate_kernel projects division-free only for chunks whose 512 voxel centres lie in a safe depth
+    range (origin depth above FrameDev::z_safe, about 13 voxels); every other chunk takes the reference's own
+    three ops in a compact loop.  The culling never lists such chunks at fine resolutions, the list form
+    (de-integration, ReIntegrateKeyframe over validChunks) can: a camera moved INTO the fused surface
+    integrates over every chunk of the map — chunks behind it (negative depths), cut by its plane (zero and
+    tiny depths, quotients of either sign and any size) and in front of it — single frames with and without
+    colour and a three-frame group, against the oracle bit for bit."""
+    seq = room_sequence(4, start=40)
+    cam = seq.cam
+    g = capi.Map(res, max_frames=16)
+    o = OracleMap(res)
+    first = seq.frames[0]
+    g.upload_frame(first.index, first.depth, None, None)
+    g.integrate_frame(first.index, False, first.pose, cam)
+    o.integrate_frame(first.depth, None, None, first.pose, cam, -1)
+    ids = g.list_chunks()
+    assert len(ids) > 100
+    # a camera on the first frame's central ray, a few voxels in front of / behind the surface it saw
+    d_c = float(first.depth[cam.height // 2, cam.width // 2])
+    yy, xx = np.mgrid[0:cam.height, 0:cam.width]
+    n_slow = n_upd = 0
+    for k, back in enumerate((6 * res, 20 * res, -4 * res)):
+        pose = np.array(first.pose, np.float32).copy()
+        pose[:3, 3] += pose[:3, 2] * np.float32(d_c - back)
+        z = ((ids.astype(np.float64) * 8 * res - pose[:3, 3].astype(np.float64)) @ pose[:3, :3].astype(np.float64))[:, 2]
+        n_slow += int(np.count_nonzero(z < 13 * res))
+        depth = (abs(back) + 3 * res * (xx / cam.width) + 2 * res * (yy / cam.height)).astype(np.float32)
+        color = k != 1
+        rgba = seq.frames[2].rgba() if color else None
+        quality = seq.frames[2].quality if color else None
+        fi = 100 + k
+        g.upload_frame(fi, depth, rgba, quality)
+        nu, q = g.integrate(fi, color, pose, cam, ids, 1)
+        onu, oq = o.integrate(depth, rgba, quality, pose, cam, ids, 1, fi if color else -1)
+        assert np.array_equal(nu, onu), f"needsUpdate differs for camera offset {back}"
+        assert np.array_equal(q.view(np.uint32)[nu != 0], np.asarray(oq, np.float32).view(np.uint32)[nu != 0])
+        n_upd += int(np.count_nonzero(nu))
+    assert n_slow > 0 and n_upd > 0
+    # the same three frames as one group (the group kernel), de-integrated
+    poses = []
+    for k, back in enumerate((6 * res, 20 * res, -4 * res)):
+        pose = np.array(first.pose, np.float32).copy()
+        pose[:3, 3] += pose[:3, 2] * np.float32(d_c - back)
+        poses.append(pose)
+    nu, q = g.integrate_group([(100, True, 0, poses[0]), (101, False, 0, poses[1]), (102, False, 0, poses[2])], cam, ids)
+    depths = [(abs(back) + 3 * res * (xx / cam.width) + 2 * res * (yy / cam.height)).astype(np.float32) for back in (6 * res, 20 * res, -4 * res)]
+    onu, _ = o.integrate(depths[0], seq.frames[2].rgba(), seq.frames[2].quality, poses[0], cam, ids, 0, 100)
+    onu, _ = o.integrate(depths[1], None, None, poses[1], cam, ids, 0, -1, onu)
+    onu, _ = o.integrate(depths[2], None, None, poses[2], cam, ids, 0, -1, onu)
+    assert np.array_equal(nu != 0, np.asarray(onu) != 0)
+    assert assert_maps_equal(g, o, what="chunks at the camera plane")
+    g.close()
+
+
 def test_noisy_depth_sequence_bit_exact():
     """Gaussian depth noise (sigma 2 mm) makes pixel roundings, band edges and the early-exit rows
     irregular; fused frames and a three-frame group against the oracle at 5 mm."""
