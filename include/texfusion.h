@@ -304,6 +304,12 @@ int tf_atlas_update(tf_map* m, const tf_patch_desc* patches, int64_t n);
 /* texture_buffer rows for the GL upload (GCFusion/MobileFusion.h:404-427): bytes
  * [hot_start*3, hot_end*3) of the 13824x13824x3 atlas, hot_* in pixels as Atlas::hot_start. */
 int tf_atlas_download(tf_map* m, uint64_t hot_start, uint64_t hot_end, uint8_t* rgb_out);
+/* The same bytes copied device to device into dst_device (device memory of any GPU of the process),
+ * complete on return: the CUDA side of a CUDA-GL interop upload.  The caller registers its pixel-unpack
+ * buffer once (cudaGraphicsGLRegisterBuffer), maps it, passes the mapped pointer here and unmaps it before
+ * glTexSubImage2D — replacing glBufferDataARB(&texture_buffer.data[hot_start*3]) of
+ * GCFusion/MobileFusion.h:406-412 (binding shown in INTEGRATION.md). */
+int tf_atlas_copy_to_device(tf_map* m, uint64_t hot_start, uint64_t hot_end, void* dst_device);
 int tf_atlas_patch_size(tf_map* m, int32_t* patch_w, int32_t* patch_h);
 
 /* Patch::CalculateTexCoords (Structure/Patch.cpp:40-108, bilinear :110-146, bilinear_depth

@@ -98,6 +98,15 @@ def test_gpu_atlas_matches_oracle_and_cv2(res):
     got = c.atlas.texture_rows(0, hot_end)
     want = o.atlas_download(0, hot_end)
     assert np.array_equal(got, want), "atlas bytes differ from the oracle"
+    # the same rows device to device (what a CUDA-GL pixel-unpack buffer receives, MobileFusion.h:404-427)
+    import torch
+    half = (hot_end // 2 // ATLAS) * ATLAS
+    pbo = torch.zeros((hot_end - half) * 3 + 64, dtype=torch.uint8, device="cuda")
+    c.map.atlas_copy_to_device(half, hot_end, pbo.data_ptr())
+    back = pbo.cpu().numpy()
+    assert np.array_equal(back[:(hot_end - half) * 3], want.reshape(-1)[half * 3:]) and not back[(hot_end - half) * 3:].any()
+    with pytest.raises(capi.TexFusionError):
+        c.map.atlas_copy_to_device(0, hot_end, got.ctypes.data)  # a host pointer
     img = got.reshape(-1, ATLAS, 3)
     for cid, (x, y, w, h) in list(zip(ids, boxes))[:60]:
         loc = c.atlas._patches[cid]["texloc"]

@@ -23,7 +23,7 @@ EXPORTS = [
     "tf_comm_unique_id", "tf_comm_init", "tf_broadcast_frame",
     "tf_prepare", "tf_integrate", "tf_integrate_group", "tf_remove_chunks", "tf_integrate_frame", "tf_integrate_frame_begin", "tf_integrate_frame_end",
     "tf_stream_step", "tf_integrate_batch", "tf_mesh_chunks", "tf_has_chunk", "tf_chunk_count", "tf_list_chunks", "tf_download_chunks",
-    "tf_atlas_alloc_slot", "tf_atlas_update", "tf_atlas_download", "tf_atlas_patch_size", "tf_patch_texcoords", "tf_sync", "tf_wait_upload",
+    "tf_atlas_alloc_slot", "tf_atlas_update", "tf_atlas_download", "tf_atlas_copy_to_device", "tf_atlas_patch_size", "tf_patch_texcoords", "tf_sync", "tf_wait_upload",
     "tf_pre_upload_depth_u16", "tf_pre_bilateral", "tf_pre_normal_map", "tf_pre_refine_keyframe", "tf_pre_refine_newframe", "tf_pre_refine_depth_by_normal", "tf_pre_color_quality",
     "tf_pre_download",
     "tf_get_counters", "tf_stream", "tf_copy_stream", "tf_set_profiling", "tf_get_kernel_time", "tf_get_stage_times", "tf_debug_project", "tf_debug_divide",
@@ -142,6 +142,7 @@ def load() -> C.CDLL:
     L.tf_atlas_alloc_slot.argtypes = [vp, ChunkId, C.POINTER(C.c_uint64)]
     L.tf_atlas_update.argtypes = [vp, C.POINTER(PatchDesc), i64]
     L.tf_atlas_download.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
+    L.tf_atlas_copy_to_device.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
     L.tf_atlas_patch_size.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.tf_patch_texcoords.argtypes = [vp, C.c_int32, C.POINTER(Pose), C.POINTER(Camera), i64, vp, vp, vp, vp, vp, vp]
     camp = C.POINTER(Camera)
@@ -473,6 +474,10 @@ class Map:
         out = np.empty((hot_end - hot_start) * 3, np.uint8)
         self._check(self.L.tf_atlas_download(self.h, C.c_uint64(hot_start), C.c_uint64(hot_end), _p(out)))
         return out
+
+    def atlas_copy_to_device(self, hot_start, hot_end, device_ptr: int):
+        """Hot rows device to device (the CUDA side of a CUDA-GL pixel-unpack-buffer upload)."""
+        self._check(self.L.tf_atlas_copy_to_device(self.h, int(hot_start), int(hot_end), C.c_void_p(device_ptr)))
 
     def patch_texcoords(self, frame_index, world_to_camera, cam, offsets, vertices, colors):
         """Patch::CalculateTexCoords for a batch of meshes; returns (texcoord, texcolor, results[n,6])."""

@@ -1762,6 +1762,28 @@ int tf_atlas_download(tf_map* m, uint64_t hot_start, uint64_t hot_end, uint8_t* 
   return TF_OK;
 }
 
+// The same rows device to device: the caller's pixel-unpack buffer, registered with CUDA
+// (cudaGraphicsGLRegisterBuffer) and mapped, takes the place of glBufferDataARB's host pointer — the
+// texture bytes never leave the GPU.
+int tf_atlas_copy_to_device(tf_map* m, uint64_t hot_start, uint64_t hot_end, void* dst_device) {
+  if (!m || !dst_device || hot_end < hot_start || hot_end > (uint64_t)kAtlasDim * kAtlasDim)
+    return fail(m, TF_ERR_INVALID, "tf_atlas_copy_to_device: bad range");
+  use_device(m);
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, dst_device) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+    cudaGetLastError();
+    return fail(m, TF_ERR_INVALID, "tf_atlas_copy_to_device: destination is not device memory");
+  }
+  if (int rc = ensure_atlas(m)) return rc;
+  const size_t nb = (size_t)(hot_end - hot_start) * 3;
+  if (at.device == m->cfg.device)
+    CUDA_OK(m, cudaMemcpyAsync(dst_device, m->atlas + hot_start * 3, nb, cudaMemcpyDeviceToDevice, m->stream));
+  else  // the display GPU is another device than the map's
+    CUDA_OK(m, cudaMemcpyPeerAsync(dst_device, at.device, m->atlas + hot_start * 3, m->cfg.device, nb, m->stream));
+  CUDA_OK(m, cudaStreamSynchronize(m->stream));  // the caller unmaps the resource right after
+  return TF_OK;
+}
+
 // Patch::CalculateTexCoords for a batch of chunk meshes against one key-frame of the store.
 int tf_patch_texcoords(tf_map* m, int32_t frame_index, const tf_pose* world_to_camera, const tf_camera* cam,
                        int64_t n_patches, const int64_t* vertex_offsets, const float* vertices, const float* colors,

@@ -513,6 +513,15 @@ class Atlas {
     const int rc = tf_atlas_download(map, hot_start, end, host_pixels + hot_start * 3);
     if (rc < 0) throw TexFusionError(rc, tf_last_error(map));
   }
+  // The hot rows straight into a mapped CUDA-GL pixel-unpack buffer (device pointer from
+  // cudaGraphicsResourceGetMappedPointer): replaces glBufferDataARB(&texture_buffer.data[hot_start*3]) of
+  // GCFusion/MobileFusion.h:406-412 without the detour over the host.
+  void CopyHotRangeToDevice(void* mapped_pbo) {
+    if (hot_end <= hot_start) return;
+    const std::size_t end = std::min(hot_end, MAX_PATCH_WIDTH * MAX_PATCH_HEIGHT);
+    const int rc = tf_atlas_copy_to_device(map, hot_start, end, mapped_pbo);
+    if (rc < 0) throw TexFusionError(rc, tf_last_error(map));
+  }
   // Atlas::SaveTexturedModel (Structure/Atlas.cpp:93-179): texture_model.obj / .mtl + the atlas image.
   // With OpenCV the image is texture_material.png like the reference; without, a binary PPM
   // (texture_material.ppm, same pixels) — the .mtl names the file that was written.  `rows` limits the
