@@ -697,7 +697,7 @@ int tf_create(tf_map** out, const tf_config* cfg) {
   C_OK(cudaMalloc((void**)&m->md.pool, (size_t)max_chunks * kChunkBytes));
   C_OK(dmalloc(&m->md.slot_id, (size_t)max_chunks));
   C_OK(dmalloc(&m->md.slot_flags, (size_t)max_chunks));
-  C_OK(dmalloc(&m->md.free_stack, (size_t)max_chunks));
+  C_OK(dmalloc(&m->md.free_stack, (size_t)max_chunks + 4));  // (+4: cull_kernel stages the top in 16-byte pieces)
   C_OK(dmalloc(&m->fs, 1));
 
   m->cand_cap = 1 << 22;  // coarse candidates per frame (4^3-chunk blocks at <= 10 mm voxels)

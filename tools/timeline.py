@@ -111,7 +111,7 @@ def main():
     tr = np.nanmean(np.stack(traces2), axis=0)
     print("cull per-warp trace (warp 0 of blocks 0,37,...)")
     for k, nm in enumerate(["waited", "grid known", "coarse tested", "coarse sync", "fine tested", "chunks resolved",
-                            "list pos known", "task done", "round done"]):
+                            "list pos known", "task done", "round done", "bbox words loaded", "block synced"]):
         print(f"  {nm:18s} " + " ".join(f"{tr[b, k]:6.1f}" for b in range(0, 16)))
     tr = np.nanmean(np.stack(traces), axis=0)
     names_t = ["kernel n known", "loop top", "bulk issued", "p0 projected", "p0 gathered", "p0 chunk arrived", "p0 updated",
