@@ -1,4 +1,5 @@
-for v in texturefusion_b200/libtexfusion_b200.so; do
+for v in texturefusion_b200/libtexfusion_b200.so build/variants/dyn.so; do
+  echo "== lib=$v"
   for a in "" "--steps 20 --warmup 5"; do
   TEXFUSION_B200_LIB=$PWD/$v python bench.py --no-cpu-baseline $a 2>/dev/null | python -c "
 import json,sys
