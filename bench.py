@@ -6,7 +6,7 @@ sequence (300 poses, every 10th frame a key-frame with colour + quality, the oth
 depth-only) fused at 0.005 m voxels.  One "step" = one frame through
 Prepare + Integrate + Finalize (MobileFusion::IntegrateFrame, GCFusion/MobileFusion.cpp:223-250).
 
-  value     frames/s with the frames already resident in HBM (device-event timed)
+  value     frames/s with the frames already resident in HBM (CUDA events around the step's kernels)
   e2e       frames/s through the public C ABI with HOST (pinned) buffers: H2D of the frame's
             planes and D2H of the chunk list / flags / quality sums inside the timed region
   roofline  integrate_kernel: algorithmic bytes / CUDA-event kernel time vs measured HBM peak
@@ -275,15 +275,23 @@ def main():
     barrier()
     vox = 0
     chunks = 0
+    # The step's kernels are queued between the two events (tf_integrate_frame_begin), the closing event is
+    # recorded behind them on the same stream, then the host collects the frame (tf_integrate_frame_end): the
+    # timed region is the device time of the step from an idle GPU — launch latency included, the host's
+    # completion polling not (that is part of `e2e`).
+    L, vp0 = m.L, C.c_void_p(None)
     for s in range(args.steps):
         fr = frames[k % nf]
         flush_l2(torch, flush_buf)
         torch.cuda.synchronize()
         ev_a[s].record(ext)
-        r = fuse_resident(m, k % nf)
+        rc = L.tf_integrate_frame_begin(m.h, fr.index, int(fr.is_keyframe), C.byref(poses[k % nf]), C.byref(camc), vp0, vp0, vp0, vp0, 0)
         ev_b[s].record(ext)
-        vox += r.voxel_updates
-        chunks += r.n_chunks
+        rc = rc or L.tf_integrate_frame_end(m.h, C.byref(st))
+        if rc != 0:
+            raise RuntimeError(L.tf_last_error(m.h))
+        vox += st.voxel_updates
+        chunks += st.n_chunks
         k += 1
     barrier()
     clocks = sampler.stop()

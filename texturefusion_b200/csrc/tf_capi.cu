@@ -1366,44 +1366,70 @@ static int ensure_arena(tf_map* m, bool lists, bool ids) {
 struct PendingItem {
   const tf_batch_item* it;
   int rec;          // index into batch_rec
+  unsigned seq;     // completion stamp export_kernel writes into batch_rec[rec].w
   int n_frames;
   bool color[kMaxGroupFrames];
   size_t first_event, n_events;  // profiling events of this item (m->ev_pending)
 };
 
-// synchronise, then hand the queued re-integration items their valid lists
-static int flush_batch(tf_map* m, std::vector<PendingItem>& pend) {
+// One finished re-integration item: its valid list (updated chunks, in list order) from the arena
+// into the caller's arrays.
+static int collect_item(tf_map* m, const PendingItem& p) {
+  const int4 r = m->batch_rec[p.rec];
+  if (r.x < 0) return fail(m, TF_ERR_CAPACITY, "tf_integrate_batch: result arena exhausted");
+  int rc = TF_OK;
+  const int3* ids = m->arena_ids + r.y;
+  const float* q = m->arena_q + r.y;
+  const unsigned char* upd = m->arena_upd + r.y;
+  tf_chunk_id* vout = p.it->valid_out;
+  float* qout = p.it->quality_out;
+  const int64_t cap = p.it->cap;
+  int64_t nv = 0;
+  for (int i = 0; i < r.x; i++) {
+    if (!upd[i]) continue;
+    if (nv < cap) {
+      if (vout) memcpy(&vout[nv], &ids[i], sizeof(int3));
+      if (qout) qout[nv] = q[i];
+    }
+    nv++;
+  }
+  if (p.it->n_valid_out) *p.it->n_valid_out = nv;
+  if (nv > cap && vout) rc = fail(m, TF_ERR_CAPACITY, "tf_integrate_batch: valid_out too small");
+  m->counters.d2h_bytes += (int64_t)r.x * 17 + sizeof(int4);
+  m->counters.frames_integrated += p.n_frames;
+  m->counters.voxel_updates += (int64_t)r.z * 512 * p.n_frames;
+  for (size_t e = p.first_event; e < p.first_event + p.n_events && e < m->ev_pending.size(); e++)
+    m->ev_pending[e].bytes = algorithmic_bytes(m, r.z, p.color, p.n_frames);
+  return rc;
+}
+
+// Items whose completion stamp has arrived are collected while the device works on the later ones
+// (called between the enqueues of a batch; never blocks).  `done`: items of `pend` already collected.
+static int collect_ready(tf_map* m, const std::vector<PendingItem>& pend, size_t& done) {
+  int rc = TF_OK;
+  while (done < pend.size()) {
+    const volatile int* w = &m->batch_rec[pend[done].rec].w;
+    if ((unsigned)*w != pend[done].seq) break;
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (int rc1 = collect_item(m, pend[done])) rc = rc1;
+    done++;
+  }
+  return rc;
+}
+
+// synchronise, then hand the re-integration items that have not been collected yet their valid lists
+static int flush_batch(tf_map* m, std::vector<PendingItem>& pend, size_t& done, int rc_collected) {
   publish_kernel<<<1, 1, 0, m->stream>>>(m->fs, m->res_d);  // error bits and allocator state of the whole sub-batch
   if (int rc = check_kernel(m, "publish_kernel")) return rc;
   CUDA_OK(m, cudaStreamSynchronize(m->stream));
   m->compute_done = m->compute_ticket;
   absorb_result(m);
   const int dev_err = m->res_h->error;
-  int rc = TF_OK;
-  for (const PendingItem& p : pend) {
-    const int4 r = m->batch_rec[p.rec];
-    if (r.x < 0) { rc = fail(m, TF_ERR_CAPACITY, "tf_integrate_batch: result arena exhausted"); continue; }
-    const int3* ids = m->arena_ids + r.y;
-    const float* q = m->arena_q + r.y;
-    const unsigned char* upd = m->arena_upd + r.y;
-    int64_t nv = 0;
-    for (int i = 0; i < r.x; i++) {
-      if (!upd[i]) continue;
-      if (nv < p.it->cap) {
-        if (p.it->valid_out) memcpy(&p.it->valid_out[nv], &ids[i], sizeof(int3));
-        if (p.it->quality_out) p.it->quality_out[nv] = q[i];
-      }
-      nv++;
-    }
-    if (p.it->n_valid_out) *p.it->n_valid_out = nv;
-    if (nv > p.it->cap && p.it->valid_out) rc = fail(m, TF_ERR_CAPACITY, "tf_integrate_batch: valid_out too small");
-    m->counters.d2h_bytes += (int64_t)r.x * 17 + sizeof(int4);
-    m->counters.frames_integrated += p.n_frames;
-    m->counters.voxel_updates += (int64_t)r.z * 512 * p.n_frames;
-    for (size_t e = p.first_event; e < p.first_event + p.n_events && e < m->ev_pending.size(); e++)
-      m->ev_pending[e].bytes = algorithmic_bytes(m, r.z, p.color, p.n_frames);
-  }
+  int rc = rc_collected;  // (an item collected early may already have failed: capacity of its valid_out)
+  for (; done < pend.size(); done++)
+    if (int rc1 = collect_item(m, pend[done])) rc = rc1;
   pend.clear();
+  done = 0;
   m->ids_stage_used = 0;
   prof_collect(m, 0);
   if (int rc2 = dev_error_to_code(m, dev_err)) return rc2;
@@ -1429,9 +1455,12 @@ int tf_integrate_batch(tf_map* m, const tf_batch_item* items, int64_t n_items, c
   if (int rc = ensure_setup(m, max_frames)) return rc;
   CUDA_OK(m, cudaMemsetAsync(&m->fs->arena_off, 0, sizeof(int), m->stream));
   std::vector<PendingItem> pend;
+  size_t done = 0;   // items of `pend` collected while later ones were being queued
+  int rc_early = TF_OK;
   tf_group_frame fr[kMaxGroupFrames];
   for (int64_t k = 0; k < n_items; k++) {
     const tf_batch_item& it = items[k];
+    if (int rc1 = collect_ready(m, pend, done)) rc_early = rc1;
     for (int f = 0; f < it.n_frames; f++) {
       fr[f] = it.frames[f];
       fr[f].flag = it.flag ? 1 : 0;
@@ -1445,7 +1474,8 @@ int tf_integrate_batch(tf_map* m, const tf_batch_item* items, int64_t n_items, c
       if (int rc = build_group(m, fr, it.n_frames, cam, gp, color)) return rc;
       if (it.n_ids > m->list_cap) return fail(m, TF_ERR_CAPACITY, "chunk list exceeds the list capacity");
       if (it.n_ids > kIdsStage - m->ids_stage_used) {  // staging full: drain what is queued
-        if (int rc = flush_batch(m, pend)) return rc;
+        if (int rc = flush_batch(m, pend, done, rc_early)) return rc;
+        rc_early = TF_OK;
         CUDA_OK(m, cudaMemsetAsync(&m->fs->arena_off, 0, sizeof(int), m->stream));
       }
       const tf_chunk_id* src = it.ids;
@@ -1492,6 +1522,7 @@ int tf_integrate_batch(tf_map* m, const tf_batch_item* items, int64_t n_items, c
       a.ff.out_cap = m->list_cap;
       a.ff.res = m->res_d;
       a.ff.seq = ++m->seq;
+      p.seq = a.ff.seq;
       a.ff.export_follows = 1;
       a.want_export = true;  // (without lists the export kernel only records the item's list length)
       a.ex = ExportArgs{};
@@ -1517,12 +1548,13 @@ int tf_integrate_batch(tf_map* m, const tf_batch_item* items, int64_t n_items, c
       m->counters.kernel_launches--;  // (check_kernel counted one launch too many)
       pend.push_back(p);
       if ((int)pend.size() == kSubBatch) {
-        if (int rc = flush_batch(m, pend)) return rc;
+        if (int rc = flush_batch(m, pend, done, rc_early)) return rc;
+        rc_early = TF_OK;
         CUDA_OK(m, cudaMemsetAsync(&m->fs->arena_off, 0, sizeof(int), m->stream));
       }
     }
   }
-  return flush_batch(m, pend);
+  return flush_batch(m, pend, done, rc_early);
 }
 
 #ifdef TF_TIMELINE
