@@ -193,6 +193,20 @@ def test_errors_and_edge_cases():
     assert g.chunk_count() == total - 5
     g.reset()
     assert g.chunk_count() == 0
+    # a NaN or an infinity in the depth image is reported (both pipelines), and the map stays usable
+    for k, bad_value in enumerate((np.nan, np.inf, -np.inf)):
+        bad = fr.depth.copy()
+        bad[17 + k, 33] = bad_value
+        g.upload_frame(20 + k, bad)
+        with pytest.raises(capi.TexFusionError) as e:
+            g.integrate_frame(20 + k, False, fr.pose, cam) if k != 1 else g.prepare(20 + k, fr.pose, cam)
+        assert e.value.code == capi.TF_ERR_INVALID and "NaN" in str(e.value)
+    g.reset()
+    g.upload_frame(fr.index, fr.depth)
+    st, *_ = g.integrate_frame(fr.index, False, fr.pose, cam)
+    o2 = OracleMap(res)
+    n, nupd = o2.integrate_frame(fr.depth, None, None, fr.pose, cam, -1)
+    assert (st.n_chunks, st.n_updated) == (n, nupd)
 
 
 def test_fast_projection_never_disagrees_with_exact_path():

@@ -365,6 +365,7 @@ int dev_error_to_code(tf_map* m, int e) {
   if (!e) return TF_OK;
   cudaMemsetAsync(&m->fs->error, 0, sizeof(int), m->stream);
   if (e & kErrMissing) return fail(m, TF_ERR_NOT_FOUND, "chunk id not in the map");
+  if (e & kErrDepth) return fail(m, TF_ERR_INVALID, "depth image contains an infinity or a NaN (the contract is finite depths, 0 = no measurement)");
   if (e & kErrCoord) return fail(m, TF_ERR_INVALID, "chunk coordinates outside +-2^20");
   if (e & kErrPool) return fail(m, TF_ERR_CAPACITY, "chunk pool exhausted (raise tf_config.max_chunks)");
   if (e & kErrList) return fail(m, TF_ERR_CAPACITY, "frame chunk list exceeds the list capacity");
