@@ -208,6 +208,7 @@ struct tf_map {
     float* q_out = nullptr;
     bool direct[4] = {false, false, false, false};
     uint64_t ticket = 0;
+    int n_export_blocks = 0;  // blocks of export_kernel whose stamps the host waits for (0: no lists)
   } pend;
 
   // CUDA graphs of the fused per-frame chain, one per (colour, group size); see fused_group
@@ -1063,7 +1064,7 @@ struct FrameArgs {
 // system-scope fence: a small grid finishes earlier than one block per SM.
 static int export_grid(const tf_map* m) {
   static const int g = [] { const char* e = getenv("TEXFUSION_B200_EXPORT_GRID"); return e ? atoi(e) : 0; }();
-  return g > 0 ? g : std::min(8, m->sm_count);
+  return std::min(g > 0 ? g : std::min(8, m->sm_count), kMaxExportBlocks);
 }
 
 static void launch_frame_kernels(tf_map* m, FrameArgs& a, bool profile = false) {
@@ -1148,9 +1149,14 @@ static int launch_frame_graph(tf_map* m, FrameGraph& fg, FrameArgs& a) {
 // Waits for the completion stamp of a fused frame (written last by publish_frame into mapped host
 // memory).  Polling it returns a few microseconds earlier than cudaStreamSynchronize; the stream
 // is queried now and then so that a failed kernel cannot hang the caller.
-static int wait_frame(tf_map* m, unsigned seq) {
+static int wait_frame(tf_map* m, unsigned seq, int n_export_blocks) {
   volatile FrameResultHost* r = m->res_h;
-  auto done = [&] { return r->seq == seq && r->seq0 == seq && r->seq1 == seq; };
+  auto done = [&] {
+    if (!(r->seq == seq && r->seq0 == seq && r->seq1 == seq)) return false;
+    for (int b = 0; b < n_export_blocks; b++)  // every export block's part of the lists has arrived
+      if (r->blk[b] != seq) return false;
+    return true;
+  };
   for (unsigned it = 1; !done(); it++) {
     if ((it & 0x3fffu) == 0) {
       const cudaError_t e = cudaStreamQuery(m->stream);
@@ -1245,6 +1251,7 @@ static int fused_group_begin(tf_map* m, const tf_group_frame* frames, int n_fram
   pf.graph = launched;
   pf.seq = ff.seq;
   pf.n_frames = n_frames;
+  pf.n_export_blocks = want_lists ? export_grid(m) : 0;
   pf.ocap = ocap;
   pf.ids_out = ids_out, pf.new_out = new_out, pf.upd_out = upd_out, pf.q_out = q_out;
   for (int k = 0; k < 4; k++) pf.direct[k] = direct[k] != nullptr;
@@ -1256,7 +1263,7 @@ static int fused_group_end(tf_map* m, tf_frame_stats* stats) {
   if (!pf.active) return fail(m, TF_ERR_INVALID, "tf_integrate_frame_end: no fused frame in flight");
   pf.active = false;
   if (pf.graph) {
-    if (int rc = wait_frame(m, pf.seq)) return rc;
+    if (int rc = wait_frame(m, pf.seq, pf.n_export_blocks)) return rc;
   } else {
     CUDA_OK(m, cudaStreamSynchronize(m->stream));
   }
